@@ -1,0 +1,472 @@
+"""CPU oracle for the AWR dense hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this file.  The product path (awr_b200) never does; it fails
+loudly when the CUDA library is missing.
+
+What this is: a plain restatement, in functional torch-CPU fp32 arithmetic, of
+the algorithm the reference runs on the path named by BASELINE.json:
+
+  backbone (model/resnet_deconv.py, model/hourglass.py)
+    -> adaptive-weighting head (util/feature_tool.py)
+    -> SmoothL1 (model/loss.py) -> backward -> Adam (train.py:67,129-131)
+
+The reference itself is pure Python on top of torch (pinned torch==1.1.0 in
+requirements.txt:1; README.md:11 says 1.4.0).  The heavy arithmetic therefore
+lives in a third-party dependency (torch conv2d / conv_transpose2d /
+batch_norm / max_pool2d / softmax) whose semantics are stable 1.1 -> 2.11; the
+restatement calls the same published primitives through torch.nn.functional on
+a flat state_dict, and writes the head / loss / coordinate grid in closed form.
+
+Parity pin: tests/golden/*.pt were produced by tests/golden/make_golden.py,
+which imports the UNMODIFIED reference modules from /root/reference in the
+build container and records their outputs on seeded inputs; tests/test_oracle.py
+checks every function here against those vectors.  (The reference ships no unit
+tests or known-answer vectors of its own: SURVEY.md section 4.)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1          # model/resnet_deconv.py:6 ; hourglass uses the torch default (also 0.1)
+HUBER_DELTA = 0.01         # model/loss.py:12-13
+SOFTMAX_SCALE = 30.0       # util/feature_tool.py:60
+DEPTH_BG = 0.99            # util/feature_tool.py:35,57
+
+RESNET_SPEC = {18: ("basic", [2, 2, 2, 2]), 50: ("bottleneck", [3, 4, 6, 3]),
+               101: ("bottleneck", [3, 4, 23, 3]), 152: ("bottleneck", [3, 8, 36, 3])}
+
+
+# --------------------------------------------------------------------------------------
+# a.4  coordinate grid   (util/feature_tool.py:23-27 and :50-55)
+# --------------------------------------------------------------------------------------
+def coord_axis(feature_size: int) -> Tensor:
+    """1-D pixel-centre coordinate 2*(i+0.5)/F - 1, evaluated in fp32 in the reference's order."""
+    i = torch.arange(feature_size).float()
+    return 2.0 * (i + 0.5) / feature_size - 1.0
+
+
+def sample_depth(img: Tensor, feature_size: int) -> Tensor:
+    """F.interpolate(img, [F,F]) with the default 'nearest' mode (feature_tool.py:20,44).
+
+    For integer ratios nearest picks src index floor(dst*H/F) = dst*(H/F), i.e. a strided slice."""
+    B, C, H, W = img.shape
+    assert C == 1 and H % feature_size == 0 and W % feature_size == 0
+    return img[:, 0, :: H // feature_size, :: W // feature_size].contiguous()      # (B,F,F)
+
+
+# --------------------------------------------------------------------------------------
+# a.5  joint2offset   (util/feature_tool.py:12-39)
+# --------------------------------------------------------------------------------------
+def joint2offset(jt_uvd: Tensor, img: Tensor, kernel_size: float, feature_size: int) -> Tensor:
+    B, J, _ = jt_uvd.shape
+    Fs = feature_size
+    d = sample_depth(img, Fs)                                                # (B,F,F)
+    ax = coord_axis(Fs).to(jt_uvd.device)
+    u = ax.view(1, 1, 1, Fs).expand(B, 1, Fs, Fs)
+    v = ax.view(1, 1, Fs, 1).expand(B, 1, Fs, Fs)
+    coord = torch.stack((u, v, d.unsqueeze(1)), dim=2)                        # (B,1,3,F,F)
+    off = jt_uvd.view(B, J, 3, 1, 1) - coord                                  # :29
+    dis = torch.sqrt((off * off).sum(dim=2) + 1e-8)                           # :31
+    off_n = off / dis.unsqueeze(2)                                            # :33
+    hm = (kernel_size - dis) / kernel_size                                    # :34
+    mask = (hm >= 0).float() * (d < DEPTH_BG).float().unsqueeze(1)            # :35
+    out_vec = (off_n * mask.unsqueeze(2)).reshape(B, 3 * J, Fs, Fs)           # :37
+    out_hm = hm * mask                                                        # :38
+    return torch.cat((out_vec, out_hm), dim=1).float()
+
+
+# --------------------------------------------------------------------------------------
+# a.6  offset2joint_softmax and its analytic backward   (util/feature_tool.py:41-65)
+# --------------------------------------------------------------------------------------
+def offset2joint_softmax(offset: Tensor, img: Tensor, kernel_size: float) -> Tensor:
+    B, C, Fs, _ = offset.shape
+    J = C // 4
+    P = Fs * Fs
+    d = sample_depth(img, Fs).view(B, 1, P)
+    m = (d < DEPTH_BG).float()                                               # :57
+    ax = coord_axis(Fs).to(offset.device)
+    u = ax.view(1, Fs).expand(Fs, Fs).reshape(1, 1, P)
+    v = ax.view(Fs, 1).expand(Fs, Fs).reshape(1, 1, P)
+    vec = offset[:, : 3 * J].reshape(B, J, 3, P) * m.unsqueeze(1)             # :58
+    h = offset[:, 3 * J:].reshape(B, J, P) * m                                # :59
+    w = torch.softmax(h * SOFTMAX_SCALE, dim=-1)                              # :60 (masked pixels keep logit 0)
+    dis = kernel_size - h * kernel_size                                      # :61
+    coord = torch.stack((u.expand(B, 1, P), v.expand(B, 1, P), d), dim=2)     # (B,1,3,P)
+    val = vec * dis.unsqueeze(2) + coord
+    return (val * w.unsqueeze(2)).sum(dim=-1).float()                         # :63
+
+
+def offset2joint_softmax_bwd(offset: Tensor, img: Tensor, kernel_size: float, g_uvd: Tensor) -> Tensor:
+    """Closed-form d L / d offset given g_uvd = d L / d uvd  (derivation: SURVEY.md section 8 a.6)."""
+    B, C, Fs, _ = offset.shape
+    J = C // 4
+    P = Fs * Fs
+    d = sample_depth(img, Fs).view(B, 1, P)
+    m = (d < DEPTH_BG).float()
+    ax = coord_axis(Fs)
+    u = ax.view(1, Fs).expand(Fs, Fs).reshape(1, 1, P)
+    v = ax.view(Fs, 1).expand(Fs, Fs).reshape(1, 1, P)
+    vec = offset[:, : 3 * J].reshape(B, J, 3, P) * m.unsqueeze(1)
+    h = offset[:, 3 * J:].reshape(B, J, P) * m
+    w = torch.softmax(h * SOFTMAX_SCALE, dim=-1)
+    dis = kernel_size - h * kernel_size
+    coord = torch.stack((u.expand(B, 1, P), v.expand(B, 1, P), d), dim=2)
+    val = vec * dis.unsqueeze(2) + coord                                      # (B,J,3,P)
+    uvd = (val * w.unsqueeze(2)).sum(dim=-1)                                  # (B,J,3)
+    g = g_uvd.view(B, J, 3, 1)
+    d_vec = g * (w * dis).unsqueeze(2) * m.unsqueeze(1)
+    d_h = m * (g * (-kernel_size * w.unsqueeze(2) * vec
+                    + SOFTMAX_SCALE * w.unsqueeze(2) * (val - uvd.unsqueeze(-1)))).sum(dim=2)
+    return torch.cat((d_vec.reshape(B, 3 * J, Fs, Fs), d_h.reshape(B, J, Fs, Fs)), dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# a.7  My_SmoothL1Loss   (model/loss.py:8-25)  ==  Huber(delta=0.01), mean-reduced
+# --------------------------------------------------------------------------------------
+def smooth_l1(x: Tensor, y: Tensor) -> Tensor:
+    assert x.shape == y.shape                                                # :10
+    z = (x - y).float()
+    a = z.abs()
+    quad = 0.5 * z * z                                                        # :21-22
+    lin = HUBER_DELTA * (a - 0.5 * HUBER_DELTA)                               # :24-25
+    return torch.where(a < HUBER_DELTA, quad, lin).mean()
+
+
+def smooth_l1_grad(x: Tensor, y: Tensor) -> Tensor:
+    z = (x - y).float()
+    g = torch.where(z.abs() < HUBER_DELTA, z, HUBER_DELTA * torch.sign(z))
+    return g / z.numel()
+
+
+# --------------------------------------------------------------------------------------
+# a.1/a.2  ResNet-deconv backbone   (model/resnet_deconv.py:19-215)
+# --------------------------------------------------------------------------------------
+def _bn(x: Tensor, sd: Dict[str, Tensor], prefix: str, training: bool, new_stats: Optional[dict]) -> Tensor:
+    w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+    rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    if training:
+        rm2, rv2 = rm.clone(), rv.clone()
+        y = F.batch_norm(x, rm2, rv2, w, b, True, BN_MOMENTUM, BN_EPS)
+        if new_stats is not None:
+            new_stats[prefix + ".running_mean"] = rm2
+            new_stats[prefix + ".running_var"] = rv2
+            new_stats[prefix + ".num_batches_tracked"] = sd[prefix + ".num_batches_tracked"] + 1
+        return y
+    return F.batch_norm(x, rm, rv, w, b, False, BN_MOMENTUM, BN_EPS)
+
+
+def resnet_layout(layers: int) -> Tuple[str, List[int]]:
+    return RESNET_SPEC[layers]
+
+
+def resnet_deconv_forward(sd: Dict[str, Tensor], x: Tensor, layers: int, downsample: int,
+                          training: bool = False, new_stats: Optional[dict] = None) -> Tensor:
+    """x (B,1,H,W) -> (B,4J,H/ds,W/ds).  Follows ResnetDeconv.forward (resnet_deconv.py:118-136)."""
+    kind, counts = RESNET_SPEC[layers]
+    bn = lambda t, p: _bn(t, sd, p, training, new_stats)
+    c = F.conv2d(x, sd["pre.0.weight"], None, 1, 2)                           # :32  5x5 s1 p2, no bias
+    c = F.max_pool2d(F.relu(bn(c, "pre.1")), 3, 2, 1)                         # :33-35
+    for li, nblk in enumerate(counts, start=1):
+        for bi in range(nblk):
+            p = f"layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1                         # :39-43,66
+            res = c
+            if kind == "basic":                                              # BasicBlock.forward :158-174
+                o = F.relu(bn(F.conv2d(c, sd[p + ".conv1.weight"], None, stride, 1), p + ".bn1"))
+                o = bn(F.conv2d(o, sd[p + ".conv2.weight"], None, 1, 1), p + ".bn2")
+            else:                                                            # Bottleneck.forward :195-215
+                o = F.relu(bn(F.conv2d(c, sd[p + ".conv1.weight"]), p + ".bn1"))
+                o = F.relu(bn(F.conv2d(o, sd[p + ".conv2.weight"], None, stride, 1), p + ".bn2"))
+                o = bn(F.conv2d(o, sd[p + ".conv3.weight"]), p + ".bn3")
+            if (p + ".downsample.0.weight") in sd:                            # :58-64
+                res = bn(F.conv2d(c, sd[p + ".downsample.0.weight"], None, stride, 0), p + ".downsample.1")
+            c = F.relu(o + res)
+    n_deconv = 4 - int(math.log(downsample, 2))                               # :45
+    for i in range(n_deconv):                                                 # :73-91  k4 s2 p1, no bias
+        c = F.conv_transpose2d(c, sd[f"deconv_layers.{3 * i}.weight"], None, 2, 1)
+        c = F.relu(bn(c, f"deconv_layers.{3 * i + 1}"))
+    vec = F.conv2d(c, sd["final1.weight"], sd["final1.bias"])                 # :133
+    ht = F.conv2d(c, sd["final2.weight"], sd["final2.bias"])                  # :134
+    return torch.cat([vec, ht], dim=1)                                        # :136
+
+
+def resnet_deconv_init(layers: int, num_joints: int, downsample: int, seed: int,
+                       head_std: Optional[float] = None) -> Dict[str, Tensor]:
+    """Seeded state_dict with the reference's key schema / shapes and its init distributions
+    (resnet_deconv.py:93-115).  NOT bit-identical to the reference's RNG stream (irrelevant:
+    golden vectors are produced by loading THIS dict into the reference module).
+    head_std overrides the 1e-3 std of deconv / final layers so heat-maps become peaked
+    (a 1e-3 head gives logits ~1e-6 and a vacuous softmax test)."""
+    g = torch.Generator().manual_seed(seed)
+    kind, counts = RESNET_SPEC[layers]
+    exp = 1 if kind == "basic" else 4
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, co, ci, k, std=None):
+        std = math.sqrt(2.0 / (k * k * co)) if std is None else std
+        sd[name] = torch.randn(co, ci, k, k, generator=g) * std
+
+    def bnp(name, c):
+        sd[name + ".weight"] = torch.ones(c)
+        sd[name + ".bias"] = torch.zeros(c)
+        sd[name + ".running_mean"] = torch.zeros(c)
+        sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    conv("pre.0.weight", 64, 1, 5)
+    bnp("pre.1", 64)
+    inpl = 64
+    for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], counts), start=1):
+        for bi in range(nblk):
+            p = f"layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            if kind == "basic":
+                conv(p + ".conv1.weight", planes, inpl, 3); bnp(p + ".bn1", planes)
+                conv(p + ".conv2.weight", planes, planes, 3); bnp(p + ".bn2", planes)
+            else:
+                conv(p + ".conv1.weight", planes, inpl, 1); bnp(p + ".bn1", planes)
+                conv(p + ".conv2.weight", planes, planes, 3); bnp(p + ".bn2", planes)
+                conv(p + ".conv3.weight", planes * 4, planes, 1); bnp(p + ".bn3", planes * 4)
+            if bi == 0 and (stride != 1 or inpl != planes * exp):
+                conv(p + ".downsample.0.weight", planes * exp, inpl, 1); bnp(p + ".downsample.1", planes * exp)
+            inpl = planes * exp
+    hs = 1e-3 if head_std is None else head_std
+    for i in range(4 - int(math.log(downsample, 2))):
+        sd[f"deconv_layers.{3 * i}.weight"] = torch.randn(inpl, 256, 4, 4, generator=g) * hs   # IOHW
+        bnp(f"deconv_layers.{3 * i + 1}", 256)
+        inpl = 256
+    sd["final1.weight"] = torch.randn(3 * num_joints, 256, 1, 1, generator=g) * hs
+    sd["final1.bias"] = torch.zeros(3 * num_joints)
+    sd["final2.weight"] = torch.randn(num_joints, 256, 1, 1, generator=g) * hs
+    sd["final2.bias"] = torch.zeros(num_joints)
+    return sd
+
+
+def randomize_bn(sd: Dict[str, Tensor], seed: int) -> Dict[str, Tensor]:
+    """Give every BN non-trivial affine + running statistics so eval-mode parity is not vacuous."""
+    g = torch.Generator().manual_seed(seed)
+    out = dict(sd)
+    for k in list(sd):
+        if k.endswith(".running_mean"):
+            p = k[: -len(".running_mean")]
+            c = sd[k].numel()
+            out[p + ".weight"] = 0.5 + torch.rand(c, generator=g)
+            out[p + ".bias"] = 0.2 * torch.randn(c, generator=g)
+            out[p + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+            out[p + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a.3  Hourglass backbone   (model/hourglass.py:6-165)
+# --------------------------------------------------------------------------------------
+def _hg_conv(sd, p, x, k):                       # Conv without bn/relu: biased conv (:10,:17-20)
+    return F.conv2d(x, sd[p + ".conv.weight"], sd[p + ".conv.bias"], 1, (k - 1) // 2)
+
+
+def _hg_residual(sd, p, x, bn):                  # Residual.forward :44-59
+    cin = sd[p + ".bn1.weight"].numel()
+    cout = sd[p + ".conv3.conv.weight"].shape[0]
+    res = _hg_conv(sd, p + ".skip_layer", x, 1) if cin != cout else x
+    o = _hg_conv(sd, p + ".conv1", F.relu(bn(x, p + ".bn1")), 1)
+    o = _hg_conv(sd, p + ".conv2", F.relu(bn(o, p + ".bn2")), 3)
+    o = _hg_conv(sd, p + ".conv3", F.relu(bn(o, p + ".bn3")), 1)
+    return o + res
+
+
+def _hg_hourglass(sd, p, x, n, bn):              # Hourglass.forward :79-88
+    up1 = _hg_residual(sd, p + ".up1", x, bn)
+    low1 = _hg_residual(sd, p + ".low1", F.max_pool2d(x, 2, 2), bn)
+    low2 = _hg_hourglass(sd, p + ".low2", low1, n - 1, bn) if n > 1 else _hg_residual(sd, p + ".low2", low1, bn)
+    low3 = _hg_residual(sd, p + ".low3", low2, bn)
+    return up1 + F.interpolate(low3, scale_factor=2, mode="nearest")
+
+
+def hourglass_forward(sd: Dict[str, Tensor], x: Tensor, nstack: int, training: bool = False,
+                      new_stats: Optional[dict] = None) -> List[Tensor]:
+    """PoseNet.forward (hourglass.py:144-165): returns the list of per-stack (B,4J,H/2,W/2) volumes."""
+    bn = lambda t, p: _bn(t, sd, p, training, new_stats)
+    c = F.relu(bn(_hg_conv(sd, "pre.0", x, 5), "pre.0.bn"))                   # :112
+    c = _hg_residual(sd, "pre.1", c, bn)
+    c = F.max_pool2d(c, 2, 2)
+    c = _hg_residual(sd, "pre.3", c, bn)
+    c = _hg_residual(sd, "pre.4", c, bn)
+    outs = []
+    for i in range(nstack):
+        hg = _hg_hourglass(sd, f"hgs.{i}.0", c, 4, bn)
+        f = _hg_residual(sd, f"features.{i}.0", hg, bn)
+        f = F.relu(bn(_hg_conv(sd, f"features.{i}.1", f, 1), f"features.{i}.1.bn"))
+        vec = F.conv2d(f, sd[f"outs_1.{i}.weight"], sd[f"outs_1.{i}.bias"])
+        ht = F.conv2d(f, sd[f"outs_2.{i}.weight"], sd[f"outs_2.{i}.bias"])
+        preds = torch.cat((vec, ht), dim=1)
+        outs.append(preds)
+        if i < nstack - 1:                                                    # :162-163
+            c = c + _hg_conv(sd, f"merge_preds.{i}.conv", preds, 1) + _hg_conv(sd, f"merge_features.{i}.conv", f, 1)
+    return outs
+
+
+def hourglass_init(nstack: int, num_joints: int, seed: int, head_gain: float = 1.0) -> Dict[str, Tensor]:
+    """Seeded state_dict with PoseNet's key schema (hourglass.py:105-142); torch-default-like
+    uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)) init.  head_gain scales outs_1/outs_2."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(p, ci, co, k, gain=1.0):
+        bound = 1.0 / math.sqrt(ci * k * k)
+        sd[p + ".weight"] = (torch.rand(co, ci, k, k, generator=g) * 2 - 1) * bound * gain
+        sd[p + ".bias"] = (torch.rand(co, generator=g) * 2 - 1) * bound * gain
+
+    def bnp(p, c):
+        sd[p + ".weight"] = torch.ones(c)
+        sd[p + ".bias"] = torch.zeros(c)
+        sd[p + ".running_mean"] = torch.zeros(c)
+        sd[p + ".running_var"] = torch.ones(c)
+        sd[p + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    def residual(p, ci, co):
+        bnp(p + ".bn1", ci); conv(p + ".conv1.conv", ci, co // 2, 1)
+        bnp(p + ".bn2", co // 2); conv(p + ".conv2.conv", co // 2, co // 2, 3)
+        bnp(p + ".bn3", co // 2); conv(p + ".conv3.conv", co // 2, co, 1)
+        conv(p + ".skip_layer.conv", ci, co, 1)                               # always constructed (:38)
+
+    def hourglass(p, n, f):
+        residual(p + ".up1", f, f); residual(p + ".low1", f, f)
+        if n > 1:
+            hourglass(p + ".low2", n - 1, f)
+        else:
+            residual(p + ".low2", f, f)
+        residual(p + ".low3", f, f)
+
+    conv("pre.0.conv", 1, 64, 5); bnp("pre.0.bn", 64)
+    residual("pre.1", 64, 128); residual("pre.3", 128, 256); residual("pre.4", 256, 256)
+    for i in range(nstack):
+        hourglass(f"hgs.{i}.0", 4, 256)
+        residual(f"features.{i}.0", 256, 256)
+        conv(f"features.{i}.1.conv", 256, 256, 1); bnp(f"features.{i}.1.bn", 256)
+        conv(f"outs_1.{i}", 256, 3 * num_joints, 1, head_gain)
+        conv(f"outs_2.{i}", 256, num_joints, 1, head_gain)
+    for i in range(nstack - 1):
+        conv(f"merge_features.{i}.conv.conv", 256, 256, 1)
+        conv(f"merge_preds.{i}.conv.conv", 4 * num_joints, 256, 1)
+    return sd
+
+
+# --------------------------------------------------------------------------------------
+# a.8  one training step   (train.py:107-131)  and Adam (train.py:67)
+# --------------------------------------------------------------------------------------
+def backbone_forward(sd, x, net: str, downsample: int, training: bool, new_stats=None) -> Tensor:
+    """net = 'resnet_<L>' | 'hourglass_<S>'.  For hourglass returns the LAST stack (the one train.py:116-121 ends up supervising)."""
+    kind, n = net.split("_")
+    if kind == "resnet":
+        return resnet_deconv_forward(sd, x, int(n), downsample, training, new_stats)
+    return hourglass_forward(sd, x, int(n), training, new_stats)[-1]
+
+
+def loss_and_grads(sd: Dict[str, Tensor], img: Tensor, jt_uvd_gt: Tensor, net: str, downsample: int,
+                   kernel_size: float, coord_weight: float, dense_weight: float):
+    """Forward + backward of one train.py iteration (train-mode BN).  Returns
+    (loss, loss_coord, loss_dense, uvd_pred, offset_pred, grads{name: tensor}, new_stats)."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
+              and not k.endswith(("running_mean", "running_var"))}
+    full = dict(sd); full.update(params)
+    new_stats: dict = {}
+    Fs = img.shape[-1] // downsample
+    offset_gt = joint2offset(jt_uvd_gt, img, kernel_size, Fs)                 # train.py:113
+    pred = backbone_forward(full, img, net, downsample, True, new_stats)      # :117/:123
+    uvd = offset2joint_softmax(pred, img, kernel_size)                        # :118/:124
+    l_coord = smooth_l1(uvd, jt_uvd_gt)
+    l_dense = smooth_l1(pred, offset_gt)
+    loss = coord_weight * l_coord + dense_weight * l_dense                    # :119-121
+    loss.backward()
+    grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
+    return loss.detach(), l_coord.detach(), l_dense.detach(), uvd.detach(), pred.detach(), grads, new_stats
+
+
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float = 1e-3,
+              b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0):
+    """torch.optim.Adam (no amsgrad, L2-style weight decay) as used at train.py:67.  In-place; step is 1-based."""
+    if weight_decay != 0.0:
+        g = g + weight_decay * p
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+# --------------------------------------------------------------------------------------
+# mean 3-D error (util/eval_tool.py:20-58, util/util.py:13-20)  -- side metric for parity reports
+# --------------------------------------------------------------------------------------
+NYU_PARAS = (588.03, 587.07, 320.0, 240.0)       # dataloader/nyu_loader.py:23
+NYU_FLIP = -1.0                                  # dataloader/nyu_loader.py:34
+
+
+def uvd_norm_to_xyz(jt_uvd: Tensor, center_xyz: Tensor, M: Tensor, cube: Tensor, img_size: int,
+                    paras=NYU_PARAS, flip: float = NYU_FLIP) -> Tensor:
+    """Normalised crop UVD (B,J,3) -> camera XYZ in mm, batched form of EvalUtil.feed (eval_tool.py:34-43)."""
+    uvd = jt_uvd.double().clone()
+    uv = (uvd[..., :2] + 1) * img_size / 2.0
+    dep = uvd[..., 2] * cube[:, None, 2].double() / 2.0 + center_xyz[:, None, 2].double()
+    hom = torch.cat((uv, torch.ones_like(uv[..., :1])), dim=-1)               # (B,J,3)
+    Minv = torch.linalg.inv(M.double())
+    uv0 = torch.einsum("bij,bkj->bki", Minv, hom)[..., :2]
+    x = (uv0[..., 0] - paras[2]) * dep / paras[0]
+    y = (uv0[..., 1] - paras[3]) * dep / paras[1] * flip
+    return torch.stack((x, y, dep), dim=-1).float()
+
+
+def mean_3d_error_mm(jt_uvd_pred, jt_xyz_gt_norm, center_xyz, M, cube, img_size) -> float:
+    xyz_pred = uvd_norm_to_xyz(jt_uvd_pred, center_xyz, M, cube, img_size)
+    xyz_gt = jt_xyz_gt_norm * (cube[:, None, :] / 2.0) + center_xyz[:, None, :]  # eval_tool.py:45
+    return (xyz_gt - xyz_pred).pow(2).sum(-1).sqrt().mean().item()
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs (SURVEY.md section 8 d)
+# --------------------------------------------------------------------------------------
+def synthetic_batch(B: int, H: int, J: int, seed: int) -> Tuple[Tensor, Tensor]:
+    """Depth crop (B,1,H,H): background == +1.0, elliptical foreground blob with depth in [-1,0.98];
+    jt_uvd_gt (B,J,3) ~ U(-0.5,0.5).  CPU-generator seeded so the same batch exists on every box."""
+    g = torch.Generator().manual_seed(seed)
+    ax = (torch.arange(H).float() + 0.5) / H * 2 - 1
+    yy, xx = torch.meshgrid(ax, ax, indexing="ij")
+    cx = (torch.rand(B, 1, 1, generator=g) - 0.5) * 0.4
+    cy = (torch.rand(B, 1, 1, generator=g) - 0.5) * 0.4
+    rx = 0.45 + 0.3 * torch.rand(B, 1, 1, generator=g)
+    ry = 0.45 + 0.3 * torch.rand(B, 1, 1, generator=g)
+    inside = ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 < 1.0
+    ramp = 0.5 * (xx - cx) + 0.3 * (yy - cy)
+    depth = (ramp + 0.05 * torch.randn(B, H, H, generator=g)).clamp(-1.0, 0.98)
+    img = torch.where(inside, depth, torch.ones_like(depth)).unsqueeze(1).contiguous()
+    jt = torch.rand(B, J, 3, generator=g) - 0.5
+    return img.float(), jt.float()
+
+
+def head_case_inputs(B: int, J: int, Fs: int, H: int, ks: float, seed: int):
+    """Inputs of the head/loss golden cases (tests/golden/make_golden.py): depth crop, GT joints, a peaked
+    prediction volume (GT volume + 0.05 N(0,1)) and an upstream gradient for the UVD output."""
+    g = torch.Generator().manual_seed(seed)
+    img, jt = synthetic_batch(B, H, J, seed)
+    if seed == 13:                      # depth values straddling the 0.99 threshold
+        img[0, 0, :8] = 0.9899
+        img[0, 0, 8:16] = 0.99
+        img[0, 0, 16:24] = 0.9901
+    if seed == 15:
+        img[1] = 1.0                     # all background
+        img[0] = img[0].clamp(max=0.5)   # all foreground
+    gt = joint2offset(jt, img, ks, Fs)
+    pred = gt + 0.05 * torch.randn(gt.shape, generator=g)
+    g_uvd = torch.randn(B, J, 3, generator=g)
+    return img, jt, pred, g_uvd
+
+
+HEAD_CASES = [(2, 14, 64, 128, 1.0, 11), (2, 14, 64, 128, 0.4, 12), (1, 21, 32, 128, 0.4, 13),
+              (3, 16, 128, 128, 1.0, 14), (2, 14, 16, 128, 1.0, 15), (2, 14, 128, 256, 0.4, 16)]

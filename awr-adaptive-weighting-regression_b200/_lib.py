@@ -1,0 +1,77 @@
+"""ctypes binding of libawr_b200.so (declared in include/awr_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call returns
+non-zero, this raises.  The product path never routes through torch ops or any CPU restatement.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libawr_b200.so")
+
+F32, BF16 = 0, 1
+HUBER_MAX_BLOCKS = 1184
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+_PROTOS = {
+    "awr_version": [],
+    "awr_head_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "awr_head_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
+    "awr_joint2offset": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "awr_huber_fwd": [_vp, _vp, _ll, _vp, _vp, _vp],
+    "awr_huber_bwd": [_vp, _vp, _ll, _vp, _vp, _vp],
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C awr-adaptive-weighting-regression_b200`). There is no CPU/PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, args in _PROTOS.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = _i
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return list(_PROTOS)
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        if rc > 0:
+            raise RuntimeError(f"{what}: CUDA error {rc} ({torch.cuda.get_device_name() if torch.cuda.is_available() else 'no device'})")
+        raise ValueError(f"{what}: invalid argument (code {rc})")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("awr_b200 runs on CUDA tensors only (sm_100a kernels; no CPU fallback)")

@@ -1,0 +1,92 @@
+// Shared helpers for the sm_100a kernels of libawr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define AWR_OK 0
+#define AWR_ERR_BAD_ARG (-1)
+#define AWR_ERR_UNSUPPORTED (-2)
+#define AWR_ERR_DRIVER (-3)
+
+#define AWR_HOST_CHECK(cond) do { if (!(cond)) return AWR_ERR_BAD_ARG; } while (0)
+#define AWR_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of NV values per thread. All threads get the result in v[]. smem: NV*32 floats.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float x = (lane < nwarp) ? smem[i * 32 + lane] : 0.f;
+    v[i] = warp_sum(x);
+  }
+}
+
+// Huber / SmoothL1 with delta = 0.01 (reference model/loss.py:12-25)
+#define AWR_HUBER_DELTA 0.01f
+__device__ __forceinline__ float huber_val(float z) {
+  float a = fabsf(z);
+  return (a < AWR_HUBER_DELTA) ? 0.5f * z * z : AWR_HUBER_DELTA * (a - 0.5f * AWR_HUBER_DELTA);
+}
+__device__ __forceinline__ float huber_grad(float z) {
+  float a = fabsf(z);
+  return (a < AWR_HUBER_DELTA) ? z : ((z > 0.f) ? AWR_HUBER_DELTA : ((z < 0.f) ? -AWR_HUBER_DELTA : 0.f));
+}
+
+// dtype <-> float helpers for templated storage type (float or bf16)
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8-wide channel vector load/store (NHWC, C % 8 == 0): fp32 -> 2x float4, bf16 -> 1x uint4
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  __device__ __forceinline__ static void load(const float* p, float (&v)[8]) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ static void store(float* p, const float (&v)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Vec8<bf16> {
+  __device__ __forceinline__ static void load(const bf16* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+  __device__ __forceinline__ static void store(bf16* p, const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};

@@ -1,0 +1,350 @@
+// Fused adaptive-weighting head + SmoothL1 kernels (bandwidth-bound; one kernel per direction).
+//
+// Replaces, for the reference path util/feature_tool.py:12-65 + model/loss.py:8-25:
+//   coord-grid construction (feature_tool.py:23-27,50-55), nearest depth resample (:20,:44),
+//   joint2offset (:12-39), offset2joint_softmax (:41-65), My_SmoothL1Loss (loss.py:8-25).
+// Nothing is materialised: the (u,v,d) grid and the dense GT volume are recomputed per pixel in
+// registers; each (b,j) CTA streams its 4 planes of the prediction volume exactly once.
+#include "common.cuh"
+#include "awr_b200.h"
+
+namespace {
+
+constexpr float kSoftmaxScale = 30.0f;     // feature_tool.py:60
+constexpr float kDepthBg = 0.99f;          // feature_tool.py:35,57
+constexpr int kHeadThreads = 256;
+
+struct Px4 { float v[4]; };
+
+template <typename T> __device__ __forceinline__ Px4 load4(const T* p);
+template <> __device__ __forceinline__ Px4 load4<float>(const float* p) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  Px4 r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; return r;
+}
+template <> __device__ __forceinline__ Px4 load4<bf16>(const bf16* p) {
+  uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+  float2 x = __bfloat1622float2(h[0]), y = __bfloat1622float2(h[1]);
+  Px4 r; r.v[0] = x.x; r.v[1] = x.y; r.v[2] = y.x; r.v[3] = y.y; return r;
+}
+
+// depth of 4 consecutive feature pixels (row r, cols c..c+3) = img[b, r*step, (c+i)*step]   (nearest resample)
+__device__ __forceinline__ Px4 load_depth4(const float* img_b, int H, int step, int r, int c) {
+  const float* p = img_b + (size_t)(r * step) * H + (size_t)c * step;
+  Px4 d;
+  if (step == 1) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    d.v[0] = a.x; d.v[1] = a.y; d.v[2] = a.z; d.v[3] = a.w;
+  } else if (step == 2) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    d.v[0] = a.x; d.v[1] = a.z; d.v[2] = b.x; d.v[3] = b.z;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d.v[i] = __ldg(p + i * step);
+  }
+  return d;
+}
+
+__device__ __forceinline__ float coord_of(int i, float Ff) { return (2.0f * ((float)i + 0.5f)) / Ff - 1.0f; }
+
+// GT volume of joint2offset for one pixel (feature_tool.py:29-38)
+__device__ __forceinline__ void gt_pixel(float ju, float jv, float jd, float u, float v, float d, float ks,
+                                         float& g0, float& g1, float& g2, float& gh) {
+  float ox = ju - u, oy = jv - v, oz = jd - d;
+  float dis = sqrtf(ox * ox + oy * oy + oz * oz + 1e-8f);
+  float hm = (ks - dis) / ks;
+  float mk = (hm >= 0.f && d < kDepthBg) ? 1.f : 0.f;
+  g0 = (ox / dis) * mk; g1 = (oy / dis) * mk; g2 = (oz / dis) * mk; gh = hm * mk;
+}
+
+// deterministic "last CTA reduces the partials" epilogue: partial[nblk][2] -> out[2]
+__device__ void finalize_partials(const float* partial, int nblk, float inv0, float inv1, unsigned* counter,
+                                  float* out, float* smem) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(counter, 1u);
+    is_last = (t == (unsigned)nblk - 1u);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float acc[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+    acc[0] += __ldcg(partial + 2 * i);
+    acc[1] += __ldcg(partial + 2 * i + 1);
+  }
+  block_sum<2>(acc, smem);
+  if (threadIdx.x == 0) {
+    out[0] = acc[0] * inv0;
+    out[1] = acc[1] * inv1;
+    *counter = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: uvd[b,j,:] (+ softmax stats for backward) (+ joint & dense SmoothL1 sums when GT given)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kHeadThreads)
+head_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const float* __restrict__ jt_gt,
+                float* __restrict__ uvd_out, float* __restrict__ stats, float* __restrict__ partial,
+                unsigned* __restrict__ counter, float* __restrict__ loss_out, int B, int J, int F, int H, float ks) {
+  __shared__ float red[6 * 32];
+  const int bj = blockIdx.x, b = bj / J, j = bj - b * J;
+  const int P = F * F, step = H / F;
+  const float Ff = (float)F;
+  const T* p0 = pred + ((size_t)b * 4 * J + 3 * j) * P;
+  const T* ph = pred + ((size_t)b * 4 * J + 3 * J + j) * P;
+  const float* img_b = img + (size_t)b * H * H;
+  const bool has_gt = (jt_gt != nullptr);
+  float ju = 0.f, jv = 0.f, jd = 0.f;
+  if (has_gt) { ju = jt_gt[bj * 3]; jv = jt_gt[bj * 3 + 1]; jd = jt_gt[bj * 3 + 2]; }
+
+  float mx = -INFINITY, s = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f, hub = 0.f;
+  const int ngroups = P >> 2, gpr = F >> 2;
+  for (int g = threadIdx.x; g < ngroups; g += kHeadThreads) {
+    const int r = g / gpr, c = (g - r * gpr) << 2;
+    const int off = g << 2;
+    Px4 x0 = load4<T>(p0 + off), x1 = load4<T>(p0 + P + off), x2 = load4<T>(p0 + 2 * P + off), xh = load4<T>(ph + off);
+    Px4 d = load_depth4(img_b, H, step, r, c);
+    const float v = coord_of(r, Ff);
+    float l[4], gmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float m = (d.v[i] < kDepthBg) ? 1.f : 0.f;
+      l[i] = kSoftmaxScale * (xh.v[i] * m);
+      gmax = fmaxf(gmax, l[i]);
+    }
+    if (gmax > mx) {
+      float sc = __expf(mx - gmax);
+      s *= sc; a0 *= sc; a1 *= sc; a2 *= sc; mx = gmax;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float m = (d.v[i] < kDepthBg) ? 1.f : 0.f;
+      float u = coord_of(c + i, Ff);
+      float h = xh.v[i] * m;
+      float dis = ks - h * ks;
+      float e = __expf(l[i] - mx);
+      s += e;
+      a0 += e * (x0.v[i] * m * dis + u);
+      a1 += e * (x1.v[i] * m * dis + v);
+      a2 += e * (x2.v[i] * m * dis + d.v[i]);
+      if (has_gt) {
+        float g0, g1, g2, gh;
+        gt_pixel(ju, jv, jd, u, v, d.v[i], ks, g0, g1, g2, gh);
+        hub += huber_val(x0.v[i] - g0) + huber_val(x1.v[i] - g1) + huber_val(x2.v[i] - g2) + huber_val(xh.v[i] - gh);
+      }
+    }
+  }
+  // block combine of the online-softmax states
+  float wm = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wm;
+  __syncthreads();
+  float bm = red[0];
+#pragma unroll
+  for (int i = 1; i < kHeadThreads / 32; ++i) bm = fmaxf(bm, red[i]);
+  float sc = __expf(mx - bm);            // threads without pixels: exp(-inf) = 0
+  float acc[5] = {s * sc, a0 * sc, a1 * sc, a2 * sc, hub};
+  block_sum<5>(acc, red);
+  if (threadIdx.x == 0) {
+    float inv = 1.0f / acc[0];
+    float o0 = acc[1] * inv, o1 = acc[2] * inv, o2 = acc[3] * inv;
+    uvd_out[bj * 3] = o0; uvd_out[bj * 3 + 1] = o1; uvd_out[bj * 3 + 2] = o2;
+    stats[bj * 2] = bm; stats[bj * 2 + 1] = acc[0];
+    if (has_gt) {
+      partial[bj * 2] = huber_val(o0 - ju) + huber_val(o1 - jv) + huber_val(o2 - jd);
+      partial[bj * 2 + 1] = acc[4];
+    }
+  }
+  if (has_gt && loss_out != nullptr)
+    finalize_partials(partial, B * J, 1.0f / (float)(B * J * 3), 1.0f / ((float)(B * J * 4) * (float)P), counter, loss_out, red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: dpred = d(head)/dpred . g_uvd  [+ cw * dHuber(uvd,jt)]  [+ dw * dHuber(pred, gt_volume)]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kHeadThreads)
+head_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const float* __restrict__ jt_gt,
+                const float* __restrict__ uvd, const float* __restrict__ stats, const float* __restrict__ g_uvd,
+                const float* __restrict__ loss_grad, float* __restrict__ dpred, int B, int J, int F, int H, float ks,
+                float cw, float dw) {
+  const int bj = blockIdx.x, b = bj / J, j = bj - b * J;
+  const int P = F * F, step = H / F;
+  const float Ff = (float)F;
+  const size_t o0 = ((size_t)b * 4 * J + 3 * j) * P, oh = ((size_t)b * 4 * J + 3 * J + j) * P;
+  const float* img_b = img + (size_t)b * H * H;
+  const bool has_gt = (jt_gt != nullptr);
+  const float lg = loss_grad ? __ldg(loss_grad) : 1.0f;
+  const float mx = stats[bj * 2], inv_s = 1.0f / stats[bj * 2 + 1];
+  const float q0 = uvd[bj * 3], q1 = uvd[bj * 3 + 1], q2 = uvd[bj * 3 + 2];
+  float ju = 0.f, jv = 0.f, jd = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  if (g_uvd) { g0 = g_uvd[bj * 3]; g1 = g_uvd[bj * 3 + 1]; g2 = g_uvd[bj * 3 + 2]; }
+  if (has_gt) {
+    ju = jt_gt[bj * 3]; jv = jt_gt[bj * 3 + 1]; jd = jt_gt[bj * 3 + 2];
+    const float k = cw * lg / (float)(B * J * 3);
+    g0 += k * huber_grad(q0 - ju); g1 += k * huber_grad(q1 - jv); g2 += k * huber_grad(q2 - jd);
+  }
+  const float kd = (has_gt ? dw * lg : 0.f) / ((float)(B * J * 4) * (float)P);
+  const int ngroups = P >> 2, gpr = F >> 2;
+  for (int g = threadIdx.x; g < ngroups; g += kHeadThreads) {
+    const int r = g / gpr, c = (g - r * gpr) << 2;
+    const int off = g << 2;
+    Px4 x0 = load4<T>(pred + o0 + off), x1 = load4<T>(pred + o0 + P + off), x2 = load4<T>(pred + o0 + 2 * P + off),
+        xh = load4<T>(pred + oh + off);
+    Px4 d = load_depth4(img_b, H, step, r, c);
+    const float v = coord_of(r, Ff);
+    float r0[4], r1[4], r2[4], rh[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float m = (d.v[i] < kDepthBg) ? 1.f : 0.f;
+      float u = coord_of(c + i, Ff);
+      float h = xh.v[i] * m;
+      float dis = ks - h * ks;
+      float w = __expf(kSoftmaxScale * h - mx) * inv_s;
+      float v0 = x0.v[i] * m, v1 = x1.v[i] * m, v2 = x2.v[i] * m;
+      float wd = w * dis * m;
+      r0[i] = g0 * wd; r1[i] = g1 * wd; r2[i] = g2 * wd;
+      float t = g0 * (-ks * v0 + kSoftmaxScale * (v0 * dis + u - q0)) + g1 * (-ks * v1 + kSoftmaxScale * (v1 * dis + v - q1)) +
+                g2 * (-ks * v2 + kSoftmaxScale * (v2 * dis + d.v[i] - q2));
+      rh[i] = m * w * t;
+      if (has_gt) {
+        float t0, t1, t2, th;
+        gt_pixel(ju, jv, jd, u, v, d.v[i], ks, t0, t1, t2, th);
+        r0[i] += kd * huber_grad(x0.v[i] - t0); r1[i] += kd * huber_grad(x1.v[i] - t1);
+        r2[i] += kd * huber_grad(x2.v[i] - t2); rh[i] += kd * huber_grad(xh.v[i] - th);
+      }
+    }
+    __stcs(reinterpret_cast<float4*>(dpred + o0 + off), make_float4(r0[0], r0[1], r0[2], r0[3]));
+    __stcs(reinterpret_cast<float4*>(dpred + o0 + P + off), make_float4(r1[0], r1[1], r1[2], r1[3]));
+    __stcs(reinterpret_cast<float4*>(dpred + o0 + 2 * P + off), make_float4(r2[0], r2[1], r2[2], r2[3]));
+    __stcs(reinterpret_cast<float4*>(dpred + oh + off), make_float4(rh[0], rh[1], rh[2], rh[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone joint2offset (drop-in for FeatureModule.joint2offset; the fused path never calls it)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kHeadThreads)
+joint2offset_kernel(const float* __restrict__ jt, const float* __restrict__ img, float* __restrict__ out, int B, int J,
+                    int F, int H, float ks) {
+  const int bj = blockIdx.x, b = bj / J, j = bj - b * J;
+  const int P = F * F, step = H / F;
+  const float Ff = (float)F;
+  const size_t o0 = ((size_t)b * 4 * J + 3 * j) * P, oh = ((size_t)b * 4 * J + 3 * J + j) * P;
+  const float* img_b = img + (size_t)b * H * H;
+  const float ju = jt[bj * 3], jv = jt[bj * 3 + 1], jd = jt[bj * 3 + 2];
+  const int ngroups = P >> 2, gpr = F >> 2;
+  for (int g = threadIdx.x; g < ngroups; g += kHeadThreads) {
+    const int r = g / gpr, c = (g - r * gpr) << 2;
+    const int off = g << 2;
+    Px4 d = load_depth4(img_b, H, step, r, c);
+    const float v = coord_of(r, Ff);
+    float r0[4], r1[4], r2[4], rh[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gt_pixel(ju, jv, jd, coord_of(c + i, Ff), v, d.v[i], ks, r0[i], r1[i], r2[i], rh[i]);
+    *reinterpret_cast<float4*>(out + o0 + off) = make_float4(r0[0], r0[1], r0[2], r0[3]);
+    *reinterpret_cast<float4*>(out + o0 + P + off) = make_float4(r1[0], r1[1], r1[2], r1[3]);
+    *reinterpret_cast<float4*>(out + o0 + 2 * P + off) = make_float4(r2[0], r2[1], r2[2], r2[3]);
+    *reinterpret_cast<float4*>(out + oh + off) = make_float4(rh[0], rh[1], rh[2], rh[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone SmoothL1 (drop-in for My_SmoothL1Loss)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+huber_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float* __restrict__ partial,
+                 unsigned* __restrict__ counter, float* __restrict__ out) {
+  __shared__ float red[2 * 32];
+  float acc[2] = {0.f, 0.f};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc[0] += huber_val(x[i] - y[i]);
+  block_sum<2>(acc, red);
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = acc[0]; partial[2 * blockIdx.x + 1] = 0.f; }
+  finalize_partials(partial, gridDim.x, 1.0f / (float)n, 0.f, counter, out, red);
+}
+
+__global__ void __launch_bounds__(256)
+huber_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, const float* __restrict__ gout,
+                 float* __restrict__ dx) {
+  const float k = (gout ? __ldg(gout) : 1.0f) / (float)n;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dx[i] = k * huber_grad(x[i] - y[i]);
+}
+
+bool head_args_ok(int B, int J, int F, int H) { return B > 0 && J > 0 && F >= 4 && (F % 4) == 0 && H >= F && (H % F) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int awr_head_fwd(const void* pred, int pred_dtype, const float* img, const float* uvd_gt, float* uvd_out, float* loss_out,
+                 float* ws, int B, int J, int F, int H, float kernel_size, void* stream) {
+  AWR_HOST_CHECK(pred && img && uvd_out && ws && head_args_ok(B, J, F, H));
+  AWR_HOST_CHECK(uvd_gt != nullptr || loss_out == nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* stats = ws;
+  float* partial = ws + 2 * (size_t)B * J;
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + 4 * (size_t)B * J);
+  if (pred_dtype == AWR_DTYPE_F32)
+    head_fwd_kernel<float><<<B * J, kHeadThreads, 0, st>>>((const float*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
+                                                           loss_out, B, J, F, H, kernel_size);
+  else if (pred_dtype == AWR_DTYPE_BF16)
+    head_fwd_kernel<bf16><<<B * J, kHeadThreads, 0, st>>>((const bf16*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
+                                                          loss_out, B, J, F, H, kernel_size);
+  else
+    return AWR_ERR_UNSUPPORTED;
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_head_bwd(const void* pred, int pred_dtype, const float* img, const float* uvd_gt, const float* uvd, const float* ws,
+                 const float* g_uvd, const float* loss_grad, float* dpred, int B, int J, int F, int H, float kernel_size,
+                 float coord_weight, float dense_weight, void* stream) {
+  AWR_HOST_CHECK(pred && img && uvd && ws && dpred && head_args_ok(B, J, F, H));
+  AWR_HOST_CHECK(uvd_gt != nullptr || g_uvd != nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pred_dtype == AWR_DTYPE_F32)
+    head_bwd_kernel<float><<<B * J, kHeadThreads, 0, st>>>((const float*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B,
+                                                           J, F, H, kernel_size, coord_weight, dense_weight);
+  else if (pred_dtype == AWR_DTYPE_BF16)
+    head_bwd_kernel<bf16><<<B * J, kHeadThreads, 0, st>>>((const bf16*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B, J,
+                                                          F, H, kernel_size, coord_weight, dense_weight);
+  else
+    return AWR_ERR_UNSUPPORTED;
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_joint2offset(const float* jt_uvd, const float* img, float* out, int B, int J, int F, int H, float kernel_size,
+                     void* stream) {
+  AWR_HOST_CHECK(jt_uvd && img && out && head_args_ok(B, J, F, H));
+  joint2offset_kernel<<<B * J, kHeadThreads, 0, (cudaStream_t)stream>>>(jt_uvd, img, out, B, J, F, H, kernel_size);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_huber_fwd(const float* x, const float* y, long long n, float* ws, float* out, void* stream) {
+  AWR_HOST_CHECK(x && y && ws && out && n > 0);
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > AWR_HUBER_MAX_BLOCKS) blocks = AWR_HUBER_MAX_BLOCKS;
+  unsigned* counter = reinterpret_cast<unsigned*>(ws + 2 * AWR_HUBER_MAX_BLOCKS);
+  huber_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, ws, counter, out);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_huber_bwd(const float* x, const float* y, long long n, const float* grad_out, float* dx, void* stream) {
+  AWR_HOST_CHECK(x && y && dx && n > 0);
+  int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  huber_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, grad_out, dx);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+"""GPU parity: fused head / loss kernels (through the C-ABI) vs the CPU oracle and the reference golden vectors."""
+import os
+
+import pytest
+import torch
+
+from oracle import awr_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def sub(t, step=8):
+    return t[..., ::step, ::step]
+
+
+@pytest.mark.parametrize("case", O.HEAD_CASES, ids=lambda c: f"B{c[0]}J{c[1]}F{c[2]}H{c[3]}ks{c[4]}")
+def test_head_fwd_bwd_vs_oracle_and_golden(case):
+    import awr_b200
+    from awr_b200.feature_tool import head_loss_forward, head_loss_backward
+    B, J, Fs, H, ks, seed = case
+    gold = [c for c in torch.load(os.path.join(GOLD, "head_cases.pt")) if c["seed"] == seed][0]
+    img, jt, pred, g_uvd = O.head_case_inputs(B, J, Fs, H, ks, seed)
+    d = _dev()
+    FM = awr_b200.FeatureModule()
+    crit = awr_b200.My_SmoothL1Loss().cuda()
+    # --- drop-in API (mirrors train.py:113-126) ---
+    gt = FM.joint2offset(jt.to(d), img.to(d), ks, Fs)
+    gt_o = O.joint2offset(jt, img, ks, Fs)
+    assert torch.allclose(gt.cpu(), gt_o, atol=2e-6)
+    assert torch.allclose(sub(gt.cpu()), gold["gt_sub"], atol=2e-6)
+    p = pred.to(d).requires_grad_(True)
+    uvd = FM.offset2joint_softmax(p, img.to(d), ks)
+    assert uvd.shape == (B, J, 3) and uvd.dtype == torch.float32
+    assert torch.allclose(uvd.detach().cpu(), gold["uvd"], atol=1e-5)          # tolerance: fp32, 1e-5 (north star: 1e-3)
+    lc = crit(uvd, jt.to(d))
+    ld = crit(p, gt)
+    assert torch.allclose(lc.detach().cpu(), gold["l_coord"], rtol=1e-4, atol=1e-8)
+    assert torch.allclose(ld.detach().cpu(), gold["l_dense"], rtol=1e-4, atol=1e-8)
+    (gold["cw"] * lc + gold["dw"] * ld).backward()
+    ref = O.offset2joint_softmax_bwd(pred, img, ks, gold["cw"] * O.smooth_l1_grad(gold["uvd"], jt)) + gold["dw"] * O.smooth_l1_grad(pred, gt_o)
+    scale = ref.abs().max().item()
+    assert (p.grad.cpu() - ref).abs().max().item() < 2e-4 * scale + 1e-9
+    assert torch.allclose(sub(p.grad.cpu()), gold["dpred_sub"], atol=2e-4 * scale + 1e-9)
+    # upstream-gradient mode
+    p2 = pred.to(d).requires_grad_(True)
+    (FM.offset2joint_softmax(p2, img.to(d), ks) * g_uvd.to(d)).sum().backward()
+    ref2 = O.offset2joint_softmax_bwd(pred, img, ks, g_uvd)
+    assert (p2.grad.cpu() - ref2).abs().max().item() < 2e-4 * ref2.abs().max().item()
+    # --- fused one-kernel-per-direction path ---
+    uvd_f, loss_f, ws = head_loss_forward(pred.to(d), img.to(d), jt.to(d), ks)
+    assert torch.allclose(uvd_f.cpu(), gold["uvd"], atol=1e-5)
+    assert torch.allclose(loss_f[0].cpu(), gold["l_coord"], rtol=1e-4, atol=1e-8)
+    assert torch.allclose(loss_f[1].cpu(), gold["l_dense"], rtol=1e-4, atol=1e-8)
+    dp = head_loss_backward(pred.to(d), img.to(d), jt.to(d), uvd_f, ws, ks, gold["cw"], gold["dw"])
+    assert (dp.cpu() - ref).abs().max().item() < 2e-4 * scale + 1e-9
+    # second call with the same workspace (ticket must have self-reset)
+    _, loss_f2, _ = head_loss_forward(pred.to(d), img.to(d), jt.to(d), ks, ws=ws)
+    assert torch.equal(loss_f2, loss_f)
+
+
+def test_head_bf16_pred_close():
+    from awr_b200.feature_tool import head_loss_forward
+    B, J, Fs, H, ks, seed = O.HEAD_CASES[0]
+    img, jt, pred, _ = O.head_case_inputs(B, J, Fs, H, ks, seed)
+    d = _dev()
+    uvd32, _, _ = head_loss_forward(pred.to(d), img.to(d), jt.to(d), ks)
+    uvd16, _, _ = head_loss_forward(pred.to(d).bfloat16(), img.to(d), jt.to(d), ks)
+    ref = O.offset2joint_softmax(pred.bfloat16().float(), img, ks)
+    assert torch.allclose(uvd16.cpu(), ref, atol=1e-5)
+    assert (uvd16 - uvd32).abs().max().item() < 2e-2
+
+
+def test_head_full_size_properties():
+    """C2 size (B=32, J=14, F=64): size-independent properties instead of a CPU comparison.
+    (1) a volume equal to the GT volume integrates back to the GT joints when ks is small relative to spread,
+    (2) softmax weights are shift-invariant: adding a constant to every heat-map of a frame whose pixels are all
+        foreground leaves UVD unchanged up to the dis term -> checked through linearity in the offset planes."""
+    from awr_b200.feature_tool import head_loss_forward
+    import awr_b200
+    d = _dev()
+    B, J, Fs, H = 32, 14, 64, 128
+    img, jt = O.synthetic_batch(B, H, J, 5)
+    img = img.clamp(max=0.9).to(d)                     # all foreground
+    jt = (jt * 0.6).to(d)
+    FM = awr_b200.FeatureModule()
+    gt = FM.joint2offset(jt, img, 1.0, Fs)
+    uvd, loss, _ = head_loss_forward(gt, img, jt, 1.0)
+    assert loss[1].item() == 0.0                       # pred == GT volume -> dense loss exactly 0
+    # every contributing pixel votes exactly for the joint: val = off_n*dis + coord = joint wherever the mask is 1
+    assert (uvd - jt).abs().max().item() < 0.12
+    # linearity in the offset planes for fixed heat-maps: uvd(2*vec) - uvd(vec) == uvd(vec) - uvd(0*vec)
+    p0, p1, p2 = gt.clone(), gt.clone(), gt.clone()
+    p0[:, : 3 * J] = 0
+    p2[:, : 3 * J] *= 2
+    u0 = head_loss_forward(p0, img, jt, 1.0)[0]
+    u1 = head_loss_forward(p1, img, jt, 1.0)[0]
+    u2 = head_loss_forward(p2, img, jt, 1.0)[0]
+    assert torch.allclose(u2 - u1, u1 - u0, atol=1e-5)
+
+
+def test_errors():
+    import awr_b200
+    FM = awr_b200.FeatureModule()
+    with pytest.raises(RuntimeError):
+        FM.offset2joint_softmax(torch.zeros(1, 56, 64, 64), torch.zeros(1, 1, 128, 128), 1.0)   # CPU tensors: no fallback
+    with pytest.raises(AssertionError):
+        awr_b200.My_SmoothL1Loss()(torch.zeros(2, 3, device="cuda"), torch.zeros(2, 4, device="cuda"))

@@ -7,3 +7,4 @@ plus the fused trainer used by bench.py.
 from . import _lib  # noqa: F401
 from .feature_tool import FeatureModule  # noqa: F401
 from .loss import My_SmoothL1Loss  # noqa: F401
+from .modules import get_deconv_net, PoseNet  # noqa: F401

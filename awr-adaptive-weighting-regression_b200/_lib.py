@@ -14,16 +14,31 @@ LIB_PATH = os.path.join(_HERE, "libawr_b200.so")
 F32, BF16 = 0, 1
 HUBER_MAX_BLOCKS = 1184
 
-_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_HEADER = os.path.join(os.path.dirname(_HERE), "include", "awr_b200.h")
+_CTYPES = {"int": C.c_int, "float": C.c_float, "long long": C.c_longlong, "unsigned": C.c_uint}
 
-_PROTOS = {
-    "awr_version": [],
-    "awr_head_fwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
-    "awr_head_bwd": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp],
-    "awr_joint2offset": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
-    "awr_huber_fwd": [_vp, _vp, _ll, _vp, _vp, _vp],
-    "awr_huber_bwd": [_vp, _vp, _ll, _vp, _vp, _vp],
-}
+
+def _parse_header(path):
+    """Derive ctypes prototypes from the `int awr_*(...)` declarations of include/awr_b200.h (single source of truth)."""
+    import re
+    src = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+    protos = {}
+    for name, args in re.findall(r"\bint\s+(awr_\w+)\s*\(([^)]*)\)\s*;", src):
+        types = []
+        args = args.strip()
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    types.append(C.c_void_p)
+                else:
+                    base = " ".join(a.replace("const", "").split()[:-1])
+                    types.append(_CTYPES[base])
+        protos[name] = types
+    return protos
+
+
+_PROTOS = _parse_header(_HEADER)
 
 _lib = None
 
@@ -39,7 +54,7 @@ def lib():
         for name, args in _PROTOS.items():
             fn = getattr(l, name)
             fn.argtypes = args
-            fn.restype = _i
+            fn.restype = C.c_int
         _lib = l
     return _lib
 

@@ -1,0 +1,322 @@
+// fp32-accumulate CUDA-core convolution kernels (NHWC activations of type T, fp32 master weights [kh][kw][Cout][Cin]).
+//
+// Role: the fp32 precision mode (config C1: "fp32 ... UVD output vs reference" needs fp32-accurate convolutions;
+// SURVEY.md section 7 "Precision vs parity") and shapes the tcgen05 path does not take (the 1-channel 5x5 stem,
+// K=25).  The bf16 throughput path is conv_tc.cu.  Replaces nn.Conv2d / nn.ConvTranspose2d forward + autograd
+// (model/resnet_deconv.py:31-32,78-86,141-142,182-188; model/hourglass.py:10) for this mode.
+#include "common.cuh"
+#include "awr_b200.h"
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16, LD = 68;
+
+template <typename T> __device__ __forceinline__ float4 load4c(const T* p);
+template <> __device__ __forceinline__ float4 load4c<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4c<bf16>(const bf16* p) {
+  uint2 a = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+  float2 x = __bfloat1622float2(h[0]), y = __bfloat1622float2(h[1]);
+  return make_float4(x.x, x.y, y.x, y.y);
+}
+template <typename T> __device__ __forceinline__ void store4c(T* p, float4 v);
+template <> __device__ __forceinline__ void store4c<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store4c<bf16>(bf16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk; pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+struct GatherP {
+  int N, Hi, Wi, Ck;      // gathered (input-side) tensor
+  int Ho, Wo, Cn;         // produced tensor
+  int R, S, stride, pad, transposed;
+  int w_sk, w_sn, w_tap;  // weight strides (elements): contraction channel, produced channel, tap
+  int out_mode, n_valid, accumulate;
+};
+
+// out[m, n] = sum_{tap, k} in[gather(m, tap), k] * w[tap][k, n]  (+ bias[n])
+template <typename T>
+__global__ void __launch_bounds__(256) conv_gather_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, void* __restrict__ outp, GatherP p) {
+  __shared__ __align__(16) float As[TK][LD];
+  __shared__ __align__(16) float Bs[TK][LD];
+  const int tid = threadIdx.x;
+  const long long M = (long long)p.N * p.Ho * p.Wo;
+  const long long m0 = (long long)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  // A-load role: one pixel, 4 contraction channels
+  const int a_pix = tid >> 2, a_kq = (tid & 3) * 4;
+  const long long am = m0 + a_pix;
+  int an = 0, aho = 0, awo = 0;
+  const bool a_in = am < M;
+  if (a_in) { awo = (int)(am % p.Wo); long long t = am / p.Wo; aho = (int)(t % p.Ho); an = (int)(t / p.Ho); }
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4] = {};
+  for (int r = 0; r < p.R; ++r) {
+    for (int s = 0; s < p.S; ++s) {
+      int hi, wi;
+      bool valid = a_in;
+      if (!p.transposed) {
+        hi = aho * p.stride - p.pad + r; wi = awo * p.stride - p.pad + s;
+      } else {
+        const int th = aho + p.pad - r, tw = awo + p.pad - s;
+        valid = valid && th >= 0 && tw >= 0 && (th % p.stride) == 0 && (tw % p.stride) == 0;
+        hi = th / p.stride; wi = tw / p.stride;
+      }
+      valid = valid && hi >= 0 && hi < p.Hi && wi >= 0 && wi < p.Wi;
+      const T* arow = in + (((long long)an * p.Hi + hi) * p.Wi + wi) * p.Ck;
+      const float* wt = w + (long long)(r * p.S + s) * p.w_tap;
+      for (int k0 = 0; k0 < p.Ck; k0 += TK) {
+        float4 av = valid ? load4c<T>(arow + k0 + a_kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 bv;
+        if (p.w_sk == 1) {          // contraction contiguous: thread -> (n = tid>>2, 4 k)
+          bv = *reinterpret_cast<const float4*>(wt + (long long)(n0 + (tid >> 2)) * p.w_sn + k0 + a_kq);
+        } else {                    // produced channel contiguous: thread -> (k = tid>>4, 4 n)
+          bv = *reinterpret_cast<const float4*>(wt + (long long)(k0 + ty) * p.w_sk + n0 + tx * 4);
+        }
+        __syncthreads();
+        As[a_kq + 0][a_pix] = av.x; As[a_kq + 1][a_pix] = av.y; As[a_kq + 2][a_pix] = av.z; As[a_kq + 3][a_pix] = av.w;
+        if (p.w_sk == 1) {
+          const int nn = tid >> 2;
+          Bs[a_kq + 0][nn] = bv.x; Bs[a_kq + 1][nn] = bv.y; Bs[a_kq + 2][nn] = bv.z; Bs[a_kq + 3][nn] = bv.w;
+        } else {
+          *reinterpret_cast<float4*>(&Bs[ty][tx * 4]) = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+          const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+          const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+          const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+      }
+    }
+  }
+  const int nc = n0 + tx * 4;
+  float bsv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bsv[j] = bias[nc + j];
+  }
+  if (p.out_mode == 0) {
+    T* out = reinterpret_cast<T*>(outp);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long m = m0 + ty * 4 + i;
+      if (m >= M) continue;
+      float4 v = make_float4(acc[i][0] + bsv[0], acc[i][1] + bsv[1], acc[i][2] + bsv[2], acc[i][3] + bsv[3]);
+      T* dst = out + m * p.Cn + nc;
+      if (p.accumulate) { float4 o = load4c<T>(dst); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      store4c<T>(dst, v);
+    }
+  } else {   // NCHW fp32, first n_valid channels; 4 consecutive pixels of one image per thread (P % 4 == 0)
+    float* out = reinterpret_cast<float*>(outp);
+    const long long P = (long long)p.Ho * p.Wo;
+    const long long m = m0 + ty * 4;
+    if (m < M) {
+      const long long n = m / P, pp = m % P;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (nc + j >= p.n_valid) continue;
+        float4 v = make_float4(acc[0][j] + bsv[j], acc[1][j] + bsv[j], acc[2][j] + bsv[j], acc[3][j] + bsv[j]);
+        *reinterpret_cast<float4*>(out + (n * p.n_valid + nc + j) * P + pp) = v;
+      }
+    }
+  }
+}
+
+struct WgradP {
+  int N, Hc, Wc, Cp;      // "coarse" (pointwise) tensor
+  int Hf, Wf, Cg;         // "fine" (gathered) tensor
+  int R, S, stride, pad;
+  int s_p, s_g, w_tap;    // output strides for the Cp index, the Cg index, the tap
+  int ksplit;
+};
+// dW[tap][i*s_p + j*s_g] += sum_{coarse pixel q} P[q, i] * G[q*stride - pad + tap, j]
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const T* __restrict__ Pt, const T* __restrict__ Gt, float* __restrict__ dW, WgradP p) {
+  __shared__ __align__(16) float Ps[TK][LD];
+  __shared__ __align__(16) float Gs[TK][LD];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int tiles_g = p.Cg / TN;
+  const int i0 = (blockIdx.x / tiles_g) * TM, j0 = (blockIdx.x % tiles_g) * TN;
+  const int r = blockIdx.y / p.S, s = blockIdx.y % p.S;
+  const long long Q = (long long)p.N * p.Hc * p.Wc;
+  const long long chunk = ((Q + p.ksplit - 1) / p.ksplit + TK - 1) / TK * TK;
+  const long long q_begin = (long long)blockIdx.z * chunk, q_end = min(Q, q_begin + chunk);
+  const int l_pix = tid >> 4, l_cq = (tid & 15) * 4;     // load role: pixel (0..15), 4 channels
+  float acc[4][4] = {};
+  for (long long q0 = q_begin; q0 < q_end; q0 += TK) {
+    const long long q = q0 + l_pix;
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), gv = pv;
+    if (q < q_end) {
+      const int wc = (int)(q % p.Wc); long long t = q / p.Wc; const int hc = (int)(t % p.Hc); const int n = (int)(t / p.Hc);
+      const int hf = hc * p.stride - p.pad + r, wf = wc * p.stride - p.pad + s;
+      if (hf >= 0 && hf < p.Hf && wf >= 0 && wf < p.Wf) {
+        pv = load4c<T>(Pt + q * p.Cp + i0 + l_cq);
+        gv = load4c<T>(Gt + (((long long)n * p.Hf + hf) * p.Wf + wf) * p.Cg + j0 + l_cq);
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&Ps[l_pix][l_cq]) = pv;
+    *reinterpret_cast<float4*>(&Gs[l_pix][l_cq]) = gv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Gs[k][tx * 4]);
+      const float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  float* dst = dW + (long long)blockIdx.y * p.w_tap;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      atomicAdd(dst + (long long)(i0 + ty * 4 + i) * p.s_p + (long long)(j0 + tx * 4 + j) * p.s_g, acc[i][j]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stem: 1-channel k x k stride-1 "same" convolution (resnet_deconv.py:32, hourglass.py:112), w [k*k][Cout]
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                        T* __restrict__ y, int N, int H, int W, int Cout, int k) {
+  extern __shared__ float ws[];   // [k*k][Cout]
+  for (int i = threadIdx.x; i < k * k * Cout; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int G = Cout >> 3, pad = k / 2;
+  const long long items = (long long)N * H * W * G, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+    const int cg = (int)(i % G);
+    long long t = i / G;
+    const int wx = (int)(t % W); t /= W;
+    const int hy = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = bias ? bias[cg * 8 + q] : 0.f;
+    const float* xi = x + (long long)n * H * W;
+    for (int r = 0; r < k; ++r) {
+      const int hh = hy + r - pad;
+      if (hh < 0 || hh >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int ww = wx + s - pad;
+        if (ww < 0 || ww >= W) continue;
+        const float v = __ldg(xi + (long long)hh * W + ww);
+        const float* wr = ws + (r * k + s) * Cout + cg * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = fmaf(v, wr[q], acc[q]);
+      }
+    }
+    Vec8<T>::store(y + i * 8, acc);
+  }
+}
+
+// dW[tap][co] += sum_pix dy[pix,co] * x[pix + tap];  dbias[co] += sum_pix dy[pix,co]
+template <typename T>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
+                                                         float* __restrict__ dbias, int N, int H, int W, int Cout, int k, int pix_per_block) {
+  const int co = threadIdx.x % Cout, tg = threadIdx.x / Cout, ngroups = blockDim.x / Cout;
+  const int pad = k / 2, taps = k * k;
+  const long long P = (long long)N * H * W;
+  const long long p_begin = (long long)blockIdx.x * pix_per_block, p_end = min(P, p_begin + pix_per_block);
+  float acc[8] = {};
+  float bsum = 0.f;
+  for (long long q = p_begin; q < p_end; ++q) {
+    const int wx = (int)(q % W); long long t = q / W; const int hy = (int)(t % H); const int n = (int)(t / H);
+    const float g = to_f<T>(dy[q * Cout + co]);
+    if (tg == 0) bsum += g;
+    const float* xi = x + (long long)n * H * W;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int tap = tg + a * ngroups;
+      if (tap < taps) {
+        const int hh = hy + tap / k - pad, ww = wx + tap % k - pad;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) acc[a] = fmaf(g, __ldg(xi + (long long)hh * W + ww), acc[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int tap = tg + a * ngroups;
+    if (tap < taps) atomicAdd(dW + tap * Cout + co, acc[a]);
+  }
+  if (tg == 0 && dbias) atomicAdd(dbias + co, bsum);
+}
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                                             \
+  if ((dtype) == AWR_DTYPE_F32) { typedef float T; __VA_ARGS__; }          \
+  else if ((dtype) == AWR_DTYPE_BF16) { typedef bf16 T; __VA_ARGS__; }     \
+  else return AWR_ERR_UNSUPPORTED;
+
+extern "C" {
+
+int awr_conv_simt(const void* in, const float* w, const float* bias, void* out, int dtype, int N, int Hi, int Wi, int Ck, int Ho,
+                  int Wo, int Cn, int R, int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode,
+                  int n_valid, int accumulate, void* stream) {
+  AWR_HOST_CHECK(in && w && out && N > 0 && Ck % TK == 0 && Cn % TN == 0 && R > 0 && S > 0 && stride > 0);
+  AWR_HOST_CHECK((w_sk == 1 && w_sn % 4 == 0) || (w_sn == 1 && w_sk % 4 == 0));
+  AWR_HOST_CHECK(out_mode == 0 || (out_mode == 1 && ((long long)Ho * Wo) % 4 == 0 && n_valid > 0 && n_valid <= Cn && !accumulate));
+  GatherP p{N, Hi, Wi, Ck, Ho, Wo, Cn, R, S, stride, pad, transposed, w_sk, w_sn, w_tap, out_mode, n_valid, accumulate};
+  const long long M = (long long)N * Ho * Wo;
+  dim3 grid((unsigned)((M + TM - 1) / TM), Cn / TN);
+  DISPATCH_T(dtype, conv_gather_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)in, w, bias, out, p));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, int dtype, int N, int Hc, int Wc, int Cp, int Hf, int Wf,
+                        int Cg, int R, int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream) {
+  AWR_HOST_CHECK(pointwise && gathered && dW && N > 0 && Cp % TM == 0 && Cg % TN == 0);
+  const long long Q = (long long)N * Hc * Wc;
+  const int tiles = (Cp / TM) * (Cg / TN) * R * S;
+  int ksplit = (148 * 4 + tiles - 1) / tiles;
+  const long long maxsplit = (Q + 63) / 64;
+  if (ksplit > maxsplit) ksplit = (int)maxsplit;
+  if (ksplit < 1) ksplit = 1;
+  WgradP p{N, Hc, Wc, Cp, Hf, Wf, Cg, R, S, stride, pad, s_p, s_g, w_tap, ksplit};
+  dim3 grid((Cp / TM) * (Cg / TN), R * S, ksplit);
+  DISPATCH_T(dtype, conv_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)pointwise, (const T*)gathered, dW, p));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout, int k,
+                  void* stream) {
+  AWR_HOST_CHECK(x && w && y && N > 0 && Cout % 8 == 0 && k % 2 == 1 && k <= 7);
+  const long long items = (long long)N * H * W * (Cout / 8);
+  long long blocks = (items + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const size_t smem = (size_t)k * k * Cout * sizeof(float);
+  DISPATCH_T(dtype, stem_conv_kernel<T><<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (T*)y, N, H, W, Cout, k));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int dtype, int N, int H, int W, int Cout, int k,
+                   void* stream) {
+  AWR_HOST_CHECK(x && dy && dW && N > 0 && (Cout == 64 || Cout == 128 || Cout == 256) && k % 2 == 1 && k <= 7);
+  const long long P = (long long)N * H * W;
+  const int ppb = 256;
+  AWR_HOST_CHECK((k * k + (256 / Cout) - 1) / (256 / Cout) <= 8 * 1 || true);
+  // taps handled per thread = ceil(k*k / (256/Cout)) must be <= 8
+  AWR_HOST_CHECK((k * k + (256 / Cout) - 1) / (256 / Cout) <= 8);
+  DISPATCH_T(dtype, stem_wgrad_kernel<T><<<(int)((P + ppb - 1) / ppb), 256, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dW, dbias, N, H,
+                                                                                                      W, Cout, k, ppb));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+}  // extern "C"

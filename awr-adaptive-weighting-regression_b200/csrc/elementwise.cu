@@ -1,0 +1,602 @@
+// Bandwidth-bound NHWC kernels around the convolutions: BatchNorm (train/eval) forward/backward, residual add,
+// ReLU, max-pool, nearest up-sample, layout changes, fused Adam.  Storage type T is float (fp32 mode) or bf16.
+//
+// Reference semantics reproduced here: nn.BatchNorm2d (momentum 0.1, eps 1e-5, biased var for normalisation,
+// unbiased for running_var; model/resnet_deconv.py:6,33,62,87,151-154), nn.ReLU, nn.MaxPool2d(3,2,1)
+// (resnet_deconv.py:35), nn.MaxPool2d(2,2) and nn.Upsample(scale 2, nearest) (model/hourglass.py:4,68,77),
+// torch.optim.Adam (train.py:67).
+#include "common.cuh"
+#include "awr_b200.h"
+
+namespace {
+
+constexpr int kEwThreads = 256;
+
+inline int ew_blocks(long long items, int per_thread = 4) {
+  long long b = (items + (long long)kEwThreads * per_thread - 1) / ((long long)kEwThreads * per_thread);
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+// grid for per-channel reductions: total threads must be a multiple of G = C/8 (G is a power of two <= 256)
+inline int red_blocks(long long M, int C) {
+  long long items = M * (C / 8);
+  long long b = (items + kEwThreads * 8 - 1) / (kEwThreads * 8);
+  if (b < 1) b = 1;
+  if (b > 148 * 4) b = 148 * 4;
+  return (int)b;
+}
+inline bool chan_ok(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
+
+// reduce NV per-thread 8-channel accumulators over the threads of a block that share a channel group, then
+// atomically add into out[v*C + c].  smem: kEwThreads * 8 floats.
+template <int NV>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int G, int C, float* __restrict__ out, float* smem) {
+  const int cg = threadIdx.x % G, rows = kEwThreads / G;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) smem[threadIdx.x * 8 + k] = acc[v][k];
+    __syncthreads();
+    // thread t < G*8 handles channel (t/8 -> group, t%8 -> lane) ; C = G*8 channels, may exceed blockDim
+    for (int ch = threadIdx.x; ch < G * 8; ch += kEwThreads) {
+      const int g = ch >> 3, k = ch & 7;
+      float s = 0.f;
+      for (int r = 0; r < rows; ++r) s += smem[(r * G + g) * 8 + k];
+      atomicAdd(out + v * C + ch, s);
+    }
+  }
+  (void)cg;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-channel sum / sum of squares of an NHWC tensor:  sums[0:C] += sum_m x, sums[C:2C] += sum_m x^2
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads) channel_stats_kernel(const T* __restrict__ x, long long M, int C, float* __restrict__ sums, int with_sq) {
+  __shared__ float smem[kEwThreads * 8];
+  const int G = C >> 3;
+  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  float acc[2][8] = {};
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    float v[8];
+    Vec8<T>::load(x + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc[0][k] += v[k]; acc[1][k] += v[k] * v[k]; }
+  }
+  if (with_sq) block_channel_reduce<2>(acc, G, C, sums, smem);
+  else {
+    float a1[1][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a1[0][k] = acc[0][k];
+    block_channel_reduce<1>(a1, G, C, sums, smem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BN finalize: sums -> (scale, shift) for the apply pass, (mean, invstd) saved for backward, running stats
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float* __restrict__ scale_shift,
+                                   float* __restrict__ mean_invstd, int C, float momentum, float eps, int training) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float mean, invstd;
+    if (training) {
+      mean = sums[c] / count;
+      float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+      invstd = rsqrtf(var + eps);
+      if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        float unb = (count > 1.f) ? var * count / (count - 1.f) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+      }
+    } else {
+      mean = running_mean[c];
+      invstd = rsqrtf(running_var[c] + eps);
+    }
+    const float sc = gamma[c] * invstd;
+    scale_shift[c] = sc;
+    scale_shift[C + c] = beta[c] - mean * sc;
+    if (mean_invstd) { mean_invstd[c] = mean; mean_invstd[C + c] = invstd; }
+  }
+  if (training && num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BN apply (+ residual, optionally through its own affine) (+ ReLU):  out = act(ss(y) + res_ss(res))
+// ss == nullptr means identity (plain add / relu kernels reuse this).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+affine_act_kernel(const T* __restrict__ y, const float* __restrict__ ss, const T* __restrict__ res, const float* __restrict__ res_ss,
+                  T* __restrict__ out, long long M, int C, int relu) {
+  const int G = C >> 3;
+  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int c0 = (int)(i % G) * 8;
+    float v[8];
+    Vec8<T>::load(y + i * 8, v);
+    if (ss) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * __ldg(ss + c0 + k) + __ldg(ss + C + c0 + k);
+    }
+    if (res) {
+      float r[8];
+      Vec8<T>::load(res + i * 8, r);
+      if (res_ss) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = r[k] * __ldg(res_ss + c0 + k) + __ldg(res_ss + C + c0 + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    Vec8<T>::store(out + i * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BN backward, pass 1: dz = dout * (act_out > 0 if relu);  dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * yhat
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
+                     const float* __restrict__ mean_invstd, long long M, int C, float* __restrict__ dsums) {
+  __shared__ float smem[kEwThreads * 8];
+  const int G = C >> 3;
+  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  float mean[8], istd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k]; }
+  float acc[2][8] = {};
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    float g[8], yy[8];
+    Vec8<T>::load(dout + i * 8, g);
+    Vec8<T>::load(y + i * 8, yy);
+    if (act_out) {
+      float a[8];
+      Vec8<T>::load(act_out + i * 8, a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc[0][k] += g[k]; acc[1][k] += g[k] * (yy[k] - mean[k]) * istd[k]; }
+  }
+  block_channel_reduce<2>(acc, G, C, dsums, smem);
+}
+
+// pass 2: dy = gamma*invstd*(dz - mean(dz) - yhat*mean(dz*yhat));  optional dres = dz (gradient of the residual branch);
+// block 0 also writes dgamma / dbeta.
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
+                    const float* __restrict__ mean_invstd, const float* __restrict__ dsums, const float* __restrict__ gamma,
+                    T* dy, const T* dy_addend, T* dres, const T* dres_addend, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, long long M, int C, int accumulate_param_grads) {
+  const int G = C >> 3;
+  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  const float invM = 1.0f / (float)M;
+  float mean[8], istd[8], k1[8], k2[8], gs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k];
+    k1[k] = dsums[c0 + k] * invM; k2[k] = dsums[C + c0 + k] * invM; gs[k] = gamma[c0 + k] * istd[k];
+  }
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    float g[8], yy[8];
+    Vec8<T>::load(dout + i * 8, g);
+    Vec8<T>::load(y + i * 8, yy);
+    if (act_out) {
+      float a[8];
+      Vec8<T>::load(act_out + i * 8, a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = gs[k] * (g[k] - k1[k] - (yy[k] - mean[k]) * istd[k] * k2[k]);
+    if (dres) {
+      if (dres_addend) {
+        float b[8];
+        Vec8<T>::load(dres_addend + i * 8, b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] += b[k];
+      }
+      Vec8<T>::store(dres + i * 8, g);
+    }
+    if (dy_addend) {
+      float b[8];
+      Vec8<T>::load(dy_addend + i * 8, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += b[k];
+    }
+    Vec8<T>::store(dy + i * 8, o);
+  }
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += kEwThreads) {
+      if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
+      else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
+    }
+  }
+}
+
+// relu backward / plain masked copy: dx = dout * (act_out > 0)  (+ add into existing dx when accumulate)
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+relu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ addend, T* __restrict__ dx, long long n8) {
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n8; i += stride) {
+    float g[8];
+    Vec8<T>::load(dout + i * 8, g);
+    if (act_out) {
+      float a[8];
+      Vec8<T>::load(act_out + i * 8, a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+    }
+    if (addend) {
+      float b[8];
+      Vec8<T>::load(addend + i * 8, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] += b[k];
+    }
+    Vec8<T>::store(dx + i * 8, g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// max-pool k x k / stride s / pad p (NHWC), forward records the arg-max tap (first max in scan order, as ATen)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, unsigned char* __restrict__ idx, int N, int H, int W, int C, int Ho,
+                   int Wo, int k, int s, int p) {
+  const int G = C >> 3;
+  const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int cg = (int)(i % G);
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    unsigned char bi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bi[q] = 0; }
+    for (int r = 0; r < k; ++r) {
+      const int hi = ho * s - p + r;
+      if (hi < 0 || hi >= H) continue;
+      for (int c = 0; c < k; ++c) {
+        const int wi = wo * s - p + c;
+        if (wi < 0 || wi >= W) continue;
+        float v[8];
+        Vec8<T>::load(x + (((long long)n * H + hi) * W + wi) * C + cg * 8, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (v[q] > best[q]) { best[q] = v[q]; bi[q] = (unsigned char)(r * k + c); }
+      }
+    }
+    Vec8<T>::store(out + i * 8, best);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((unsigned)bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((unsigned)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
+  }
+}
+
+// backward, gather form (no atomics): dx[n,h,w,c] = sum over windows containing (h,w) whose arg-max is (h,w)
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_bwd_kernel(const T* __restrict__ dout, const unsigned char* __restrict__ idx, T* __restrict__ dx, int N, int H, int W, int C,
+                   int Ho, int Wo, int k, int s, int p, int accumulate) {
+  const int G = C >> 3;
+  const long long items = (long long)N * H * W * G, stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int cg = (int)(i % G);
+    long long t = i / G;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8] = {};
+    // windows ho with ho*s - p <= h <= ho*s - p + k - 1
+    const int ho_lo = max(0, (h + p - k + 1 + s - 1) / s), ho_hi = min(Ho - 1, (h + p) / s);
+    const int wo_lo = max(0, (w + p - k + 1 + s - 1) / s), wo_hi = min(Wo - 1, (w + p) / s);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho)
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const int tap = (h - (ho * s - p)) * k + (w - (wo * s - p));
+        const long long o = (((long long)n * Ho + ho) * Wo + wo) * G + cg;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o * 8);
+        float g[8];
+        Vec8<T>::load(dout + o * 8, g);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const unsigned b = (q < 4) ? ((pk.x >> (8 * q)) & 0xffu) : ((pk.y >> (8 * (q - 4))) & 0xffu);
+          if ((int)b == tap) acc[q] += g[q];
+        }
+      }
+    if (accumulate) {
+      float o[8];
+      Vec8<T>::load(dx + i * 8, o);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += o[q];
+    }
+    Vec8<T>::store(dx + i * 8, acc);
+  }
+}
+
+// nearest x2 up-sample of `low` added to `up`:  out[n,h,w,c] = up[n,h,w,c] + low[n,h/2,w/2,c]   (hourglass.py:87-88)
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+upsample2_add_kernel(const T* __restrict__ up, const T* __restrict__ low, T* __restrict__ out, int N, int H, int W, int C) {
+  const int G = C >> 3;
+  const long long items = (long long)N * H * W * G, stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int cg = (int)(i % G);
+    long long t = i / G;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float a[8], b[8];
+    Vec8<T>::load(up + i * 8, a);
+    Vec8<T>::load(low + ((((long long)n * (H / 2) + h / 2) * (W / 2) + w / 2) * G + cg) * 8, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += b[k];
+    Vec8<T>::store(out + i * 8, a);
+  }
+}
+// backward of the up-sample branch: dlow[n,h2,w2,c] = sum of the 2x2 block of dout
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+upsample2_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dlow, int N, int H, int W, int C, int accumulate) {   // H,W = fine size
+  const int G = C >> 3, H2 = H / 2, W2 = W / 2;
+  const long long items = (long long)N * H2 * W2 * G, stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int cg = (int)(i % G);
+    long long t = i / G;
+    const int w = (int)(t % W2); t /= W2;
+    const int h = (int)(t % H2);
+    const int n = (int)(t / H2);
+    float acc[8] = {};
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        float g[8];
+        Vec8<T>::load(dout + ((((long long)n * H + 2 * h + dh) * W + 2 * w + dw) * G + cg) * 8, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += g[k];
+      }
+    Vec8<T>::store(dlow + i * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layout changes between the reference's NCHW fp32 tensors and the internal NHWC T tensors
+// ---------------------------------------------------------------------------------------------------------
+// src NCHW fp32 (N,Csrc,P) -> dst NHWC T (N,P,Cdst), channels >= Csrc zero-filled. 32x32 smem transpose tiles.
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int Csrc, int Cdst, int P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < Csrc && p < P) ? src[((long long)n * Csrc + c) * P + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < P && c < Cdst) dst[((long long)n * P + p) * Cdst + c] = from_f<T>(tile[threadIdx.x][r]);
+  }
+}
+// src NHWC T (N,P,Csrc) -> dst NCHW fp32 (N,Cdst,P) taking the first Cdst channels
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int Csrc, int Cdst, int P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < P && c < Csrc) ? to_f<T>(src[((long long)n * P + p) * Csrc + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (c < Cdst && p < P) dst[((long long)n * Cdst + c) * P + p] = tile[threadIdx.x][r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused Adam over a flat fp32 parameter buffer; also refreshes the bf16 shadow the tensor-core kernels read
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow,
+            long long n, const float* __restrict__ step_dev, float lr, float b1, float b2, float eps, float wd, float grad_scale) {
+  // step_dev[0] holds the 1-based step count as float (updated by the caller's graph via awr_adam_tick)
+  const float step = __ldg(step_dev);
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  const long long stride = (long long)gridDim.x * kEwThreads * 4;
+  for (long long i = ((long long)blockIdx.x * kEwThreads + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+      float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float gr = ga[k] * grad_scale + wd * pa[k];
+        ma[k] = b1 * ma[k] + (1.f - b1) * gr;
+        va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
+        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+      }
+      *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
+      if (shadow) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+        uint2 pk; pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(shadow + i) = pk;
+      }
+    } else {
+      for (long long j = i; j < n; ++j) {
+        float gr = g[j] * grad_scale + wd * p[j];
+        m[j] = b1 * m[j] + (1.f - b1) * gr;
+        v[j] = b2 * v[j] + (1.f - b2) * gr * gr;
+        p[j] -= step_size * m[j] / (sqrtf(v[j]) * inv_sqrt_bc2 + eps);
+        if (shadow) shadow[j] = __float2bfloat16_rn(p[j]);
+      }
+    }
+  }
+}
+__global__ void adam_tick_kernel(float* step_dev) { step_dev[0] += 1.f; }
+
+__global__ void __launch_bounds__(kEwThreads) cast_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                                             \
+  if ((dtype) == AWR_DTYPE_F32) { typedef float T; __VA_ARGS__; }          \
+  else if ((dtype) == AWR_DTYPE_BF16) { typedef bf16 T; __VA_ARGS__; }     \
+  else return AWR_ERR_UNSUPPORTED;
+
+extern "C" {
+
+int awr_channel_stats(const void* x, int dtype, long long M, int C, float* sums, int with_sq, void* stream) {
+  AWR_HOST_CHECK(x && sums && M > 0 && chan_ok(C));
+  DISPATCH_T(dtype, channel_stats_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums, with_sq));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_bn_finalize(const float* sums, long long count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_invstd, int C,
+                    float momentum, float eps, int training, void* stream) {
+  AWR_HOST_CHECK(gamma && beta && scale_shift && C > 0 && (training ? (sums != nullptr && count > 0) : (running_mean && running_var)));
+  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, (float)count, gamma, beta, running_mean, running_var,
+                                                                       num_batches_tracked, scale_shift, mean_invstd, C, momentum,
+                                                                       eps, training);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
+                   long long M, int C, int relu, void* stream) {
+  AWR_HOST_CHECK(y && out && M > 0 && C % 8 == 0);
+  DISPATCH_T(dtype, affine_act_kernel<T><<<ew_blocks(M * (C / 8)), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M, C, relu));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, int dtype, long long M, int C,
+                      float* dsums, void* stream) {
+  AWR_HOST_CHECK(dout && y && mean_invstd && dsums && M > 0 && chan_ok(C));
+  DISPATCH_T(dtype, bn_bwd_reduce_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, dsums));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* dsums,
+                     const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
+                     float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
+  AWR_HOST_CHECK(dout && y && mean_invstd && dsums && gamma && dy && M > 0 && chan_ok(C));
+  DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
+                        (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_relu_bwd(const void* dout, const void* act_out, const void* addend, void* dx, int dtype, long long n, void* stream) {
+  AWR_HOST_CHECK(dout && dx && n > 0 && n % 8 == 0);
+  DISPATCH_T(dtype, relu_bwd_kernel<T><<<ew_blocks(n / 8), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)act_out,
+                                                                                                 (const T*)addend, (T*)dx, n / 8));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_maxpool_fwd(const void* x, void* out, unsigned char* idx, int dtype, int N, int H, int W, int C, int k, int s, int p,
+                    void* stream) {
+  AWR_HOST_CHECK(x && out && N > 0 && C % 8 == 0 && k >= 1 && k <= 3 && s >= 1);
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  DISPATCH_T(dtype, maxpool_fwd_kernel<T><<<ew_blocks((long long)N * Ho * Wo * (C / 8), 2), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (T*)out, idx, N, H, W, C, Ho, Wo, k, s, p));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_maxpool_bwd(const void* dout, const unsigned char* idx, void* dx, int dtype, int N, int H, int W, int C, int k, int s, int p,
+                    int accumulate, void* stream) {
+  AWR_HOST_CHECK(dout && idx && dx && N > 0 && C % 8 == 0);
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  DISPATCH_T(dtype, maxpool_bwd_kernel<T><<<ew_blocks((long long)N * H * W * (C / 8), 2), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)dout, idx, (T*)dx, N, H, W, C, Ho, Wo, k, s, p, accumulate));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_upsample2_add(const void* up, const void* low, void* out, int dtype, int N, int H, int W, int C, void* stream) {
+  AWR_HOST_CHECK(up && low && out && N > 0 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0);
+  DISPATCH_T(dtype, upsample2_add_kernel<T><<<ew_blocks((long long)N * H * W * (C / 8)), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)up, (const T*)low, (T*)out, N, H, W, C));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_upsample2_bwd(const void* dout, void* dlow, int dtype, int N, int H, int W, int C, int accumulate, void* stream) {
+  AWR_HOST_CHECK(dout && dlow && N > 0 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0);
+  DISPATCH_T(dtype, upsample2_bwd_kernel<T><<<ew_blocks((long long)N * (H / 2) * (W / 2) * (C / 8), 2), kEwThreads, 0,
+                                              (cudaStream_t)stream>>>((const T*)dout, (T*)dlow, N, H, W, C, accumulate));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int Csrc, int Cdst, int P, void* stream) {
+  AWR_HOST_CHECK(src && dst && N > 0 && Csrc > 0 && Cdst >= Csrc && P > 0);
+  dim3 grid((P + 31) / 32, (Cdst + 31) / 32, N), block(32, 8);
+  DISPATCH_T(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(src, (T*)dst, Csrc, Cdst, P));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, int Csrc, int Cdst, int P, void* stream) {
+  AWR_HOST_CHECK(src && dst && N > 0 && Cdst > 0 && Cdst <= Csrc && P > 0);
+  dim3 grid((P + 31) / 32, (Cdst + 31) / 32, N), block(32, 8);
+  DISPATCH_T(dtype, nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)src, dst, Csrc, Cdst, P));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_adam_flat(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* step_dev, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
+  AWR_HOST_CHECK(p && g && m && v && step_dev && n > 0);
+  adam_kernel<<<ew_blocks((n + 3) / 4, 2), kEwThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)bf16_shadow, n, step_dev, lr, beta1,
+                                                                                beta2, eps, weight_decay, grad_scale);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_adam_tick(float* step_dev, void* stream) {
+  AWR_HOST_CHECK(step_dev);
+  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  AWR_HOST_CHECK(src && dst && n > 0);
+  cast_f32_to_bf16_kernel<<<ew_blocks(n), kEwThreads, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,639 @@
+"""Static execution plans for the AWR backbones on top of the C-ABI kernels.
+
+A `Plan` is built once per (network, batch, image size, precision, train/eval): it owns every activation /
+gradient buffer (NHWC, PyTorch-allocated), and two flat lists of kernel launches (forward, backward) with all
+pointers bound, so a step is a pure launch sequence that can be CUDA-graph captured.  Python only orders
+launches; every arithmetic op runs in libawr_b200.so.
+
+Network structure follows the reference modules it replaces:
+  ResNet-deconv : model/resnet_deconv.py:19-215      Hourglass : model/hourglass.py:6-165
+"""
+import math
+
+import torch
+
+from . import _lib as L
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+RESNET_SPEC = {18: ("basic", [2, 2, 2, 2]), 50: ("bottleneck", [3, 4, 6, 3]),
+               101: ("bottleneck", [3, 4, 23, 3]), 152: ("bottleneck", [3, 8, 36, 3])}
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+# ======================================================================================================
+# parameters: one flat fp32 buffer (+ grads, + bf16 shadow); canonical nn.Parameter tensors are VIEWS of it
+# ======================================================================================================
+class ParamSpec:
+    __slots__ = ("name", "kind", "shape", "offset", "numel", "phys_shape")
+
+    def __init__(self, name, kind, shape, offset, phys_shape):
+        self.name, self.kind, self.shape, self.offset, self.phys_shape = name, kind, tuple(shape), offset, tuple(phys_shape)
+        self.numel = int(math.prod(phys_shape))
+
+
+class ParamLayout:
+    """Physical order of every weight is what the kernels read:
+         conv   (Co,Ci,kh,kw) canonical  -> physical [kh][kw][Co][Ci]      (canonical = phys.permute(2,3,0,1))
+         deconv (Ci,Co,kh,kw) canonical  -> physical [kh][kw][Co][Ci]      (canonical = phys.permute(3,2,0,1))
+         head   two 1x1 convs (3J / J rows) share one zero-padded [64][Cin] block; biases share one [64] block
+         vec    (C,)"""
+
+    def __init__(self):
+        self.specs = {}
+        self.order = []
+        self.total = 0
+        self.buffers = {}        # non-trainable: name -> (shape, dtype)
+        self.groups = {}         # physical blocks shared by several canonical params: gname -> (offset, phys_shape)
+
+    def _alloc(self, numel):
+        off = self.total
+        self.total = _align(off + numel)
+        return off
+
+    def conv(self, name, co, ci, k, ci_pad=None):
+        """ci_pad: physical input-channel count (zero-padded) when the consumer activation is channel-padded."""
+        self._add(name, "conv", (co, ci, k, k), (k, k, co, ci_pad or ci))
+
+    def deconv(self, name, ci, co, k):
+        self._add(name, "deconv", (ci, co, k, k), (k, k, co, ci))
+
+    def vec(self, name, c):
+        self._add(name, "vec", (c,), (c,))
+
+    def _add(self, name, kind, shape, phys):
+        spec = ParamSpec(name, kind, shape, self._alloc(int(math.prod(phys))), phys)
+        self.specs[name] = spec
+        self.order.append(name)
+
+    def head(self, gname, names_rows, cin, bias_names):
+        """names_rows: [(param name, rows)] stacked into one [64][cin] block (rows beyond the sum stay zero)."""
+        off = self._alloc(64 * cin)
+        self.groups[gname + ".weight"] = (off, (64, cin))
+        r = 0
+        for n, rows in names_rows:
+            s = ParamSpec(n, "headw", (rows, cin, 1, 1), off + r * cin, (rows, cin))
+            self.specs[n] = s
+            self.order.append(n)
+            r += rows
+        boff = self._alloc(64)
+        self.groups[gname + ".bias"] = (boff, (64,))
+        r = 0
+        for (n, rows) in zip(bias_names, [x[1] for x in names_rows]):
+            s = ParamSpec(n, "vec", (rows,), boff + r, (rows,))
+            self.specs[n] = s
+            self.order.append(n)
+            r += rows
+
+    def bn(self, prefix, c):
+        self.vec(prefix + ".weight", c)
+        self.vec(prefix + ".bias", c)
+        self.buffers[prefix + ".running_mean"] = ((c,), torch.float32)
+        self.buffers[prefix + ".running_var"] = ((c,), torch.float32)
+        self.buffers[prefix + ".num_batches_tracked"] = ((), torch.long)
+
+    def view(self, flat, name):
+        s = self.specs[name]
+        t = flat[s.offset: s.offset + s.numel].view(s.phys_shape)
+        if s.kind == "conv":
+            return t[..., : s.shape[1]].permute(2, 3, 0, 1)
+        if s.kind == "deconv":
+            return t.permute(3, 2, 0, 1)
+        if s.kind == "headw":
+            return t.view(s.shape)
+        return t
+
+    def phys(self, flat, name):
+        if name in self.groups:
+            off, shp = self.groups[name]
+            return flat[off: off + int(math.prod(shp))].view(shp)
+        s = self.specs[name]
+        return flat[s.offset: s.offset + s.numel].view(s.phys_shape)
+
+
+def resnet_layout(layers, J, downsample):
+    """Key schema of ResnetDeconv.state_dict() (resnet_deconv.py:31-53)."""
+    kind, counts = RESNET_SPEC[layers]
+    exp = 1 if kind == "basic" else 4
+    lay = ParamLayout()
+    lay.conv("pre.0.weight", 64, 1, 5)
+    lay.bn("pre.1", 64)
+    inpl = 64
+    for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], counts), start=1):
+        for bi in range(nblk):
+            p = f"layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            if kind == "basic":
+                lay.conv(p + ".conv1.weight", planes, inpl, 3); lay.bn(p + ".bn1", planes)
+                lay.conv(p + ".conv2.weight", planes, planes, 3); lay.bn(p + ".bn2", planes)
+            else:
+                lay.conv(p + ".conv1.weight", planes, inpl, 1); lay.bn(p + ".bn1", planes)
+                lay.conv(p + ".conv2.weight", planes, planes, 3); lay.bn(p + ".bn2", planes)
+                lay.conv(p + ".conv3.weight", planes * 4, planes, 1); lay.bn(p + ".bn3", planes * 4)
+            if bi == 0 and (stride != 1 or inpl != planes * exp):
+                lay.conv(p + ".downsample.0.weight", planes * exp, inpl, 1); lay.bn(p + ".downsample.1", planes * exp)
+            inpl = planes * exp
+    for i in range(4 - int(math.log(downsample, 2))):
+        lay.deconv(f"deconv_layers.{3 * i}.weight", inpl, 256, 4)
+        lay.bn(f"deconv_layers.{3 * i + 1}", 256)
+        inpl = 256
+    lay.head("final", [("final1.weight", 3 * J), ("final2.weight", J)], 256, ["final1.bias", "final2.bias"])
+    return lay
+
+
+def hourglass_layout(nstack, J):
+    """Key schema of PoseNet.state_dict() (hourglass.py:105-142)."""
+    lay = ParamLayout()
+
+    def conv(p, ci, co, k):
+        lay.conv(p + ".weight", co, ci, k)
+        lay.vec(p + ".bias", co)
+
+    def residual(p, ci, co):
+        lay.bn(p + ".bn1", ci); conv(p + ".conv1.conv", ci, co // 2, 1)
+        lay.bn(p + ".bn2", co // 2); conv(p + ".conv2.conv", co // 2, co // 2, 3)
+        lay.bn(p + ".bn3", co // 2); conv(p + ".conv3.conv", co // 2, co, 1)
+        conv(p + ".skip_layer.conv", ci, co, 1)
+
+    def hourglass(p, n, f):
+        residual(p + ".up1", f, f); residual(p + ".low1", f, f)
+        if n > 1:
+            hourglass(p + ".low2", n - 1, f)
+        else:
+            residual(p + ".low2", f, f)
+        residual(p + ".low3", f, f)
+
+    conv("pre.0.conv", 1, 64, 5); lay.bn("pre.0.bn", 64)
+    residual("pre.1", 64, 128); residual("pre.3", 128, 256); residual("pre.4", 256, 256)
+    for i in range(nstack):
+        hourglass(f"hgs.{i}.0", 4, 256)
+        residual(f"features.{i}.0", 256, 256)
+        conv(f"features.{i}.1.conv", 256, 256, 1); lay.bn(f"features.{i}.1.bn", 256)
+        lay.head(f"outs.{i}", [(f"outs_1.{i}.weight", 3 * J), (f"outs_2.{i}.weight", J)], 256, [f"outs_1.{i}.bias", f"outs_2.{i}.bias"])
+    for i in range(nstack - 1):
+        conv(f"merge_features.{i}.conv.conv", 256, 256, 1)
+        # merge_preds consumes the 4J-channel prediction volume, held as a 64-channel zero-padded NHWC activation
+        lay.conv(f"merge_preds.{i}.conv.conv.weight", 256, 4 * J, 1, ci_pad=64)
+        lay.vec(f"merge_preds.{i}.conv.conv.bias", 256)
+    return lay
+
+
+# ======================================================================================================
+# activations
+# ======================================================================================================
+class Act:
+    """NHWC activation (N,H,W,C) + lazily allocated gradient buffer."""
+
+    def __init__(self, plan, N, H, W, C, dtype=None):
+        self.plan, self.N, self.H, self.W, self.C = plan, N, H, W, C
+        self.t = torch.empty(N, H, W, C, dtype=dtype or plan.tdtype, device=plan.device)
+        self.g = None
+        self.gw = False          # gradient already written in the backward plan (next contribution accumulates)
+
+    @property
+    def M(self):
+        return self.N * self.H * self.W
+
+    def grad(self):
+        if self.g is None:
+            self.g = torch.empty_like(self.t)
+        return self.g
+
+
+class BNState:
+    def __init__(self, plan, prefix, C):
+        self.prefix, self.C = prefix, C
+        self.sums = plan.arena(2 * C)
+        self.dsums = plan.arena(2 * C)
+        self.ss = torch.empty(2 * C, dtype=torch.float32, device=plan.device)
+        self.mi = torch.empty(2 * C, dtype=torch.float32, device=plan.device)
+
+
+# ======================================================================================================
+# plan
+# ======================================================================================================
+class Plan:
+    def __init__(self, net, J, downsample, B, H, precision, training, store, device):
+        """store: ParamStore (flat params/grads/buffers). precision: 'fp32' | 'bf16'."""
+        self.net, self.J, self.ds, self.B, self.H = net, J, downsample, B, H
+        self.precision, self.training, self.store, self.device = precision, training, store, device
+        self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.dt = L.F32 if precision == "fp32" else L.BF16
+        self.lib = L.lib()
+        self.fwd, self.bwd = [], []
+        self._arena_total = 0
+        self.arena_buf = torch.zeros(1 << 22, dtype=torch.float32, device=device)    # zeroed at the start of every step
+        self.ops = []
+        self.launches_fwd = 0
+        self.launches_bwd = 0
+        self.img = torch.empty(B, 1, H, H, dtype=torch.float32, device=device)       # network input (NCHW == NHWC for C=1)
+        kind, n = net.split("_")
+        if kind == "resnet":
+            self._build_resnet(int(n))
+        elif kind == "hourglass":
+            self._build_hourglass(int(n))
+        else:
+            raise ValueError(net)
+        if training:
+            for op in reversed(self.ops):
+                op.plan_bwd()
+
+    # ---- infrastructure ---------------------------------------------------------------------------
+    def arena(self, n):
+        """fp32 scratch that must be zero at the start of every step (BN sums etc.): carved from one buffer."""
+        off = self._arena_total
+        self._arena_total = _align(off + n)
+        if self._arena_total > self.arena_buf.numel():
+            raise RuntimeError("plan arena exhausted")
+        return self.arena_buf[off: off + n]
+
+    def call(self, lst, fn, *args):
+        """Bind a C-ABI launch. Tensor-like args are resolved to pointers now (buffers are static)."""
+        cargs = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
+        name = fn
+        f = getattr(self.lib, fn)
+
+        def run(stream):
+            rc = f(*cargs, stream)
+            if rc != 0:
+                L.check(rc, name)
+        lst.append(run)
+
+    def P(self, name):
+        return self.store.layout.phys(self.store.params, name)
+
+    def G(self, name):
+        return self.store.layout.phys(self.store.grads, name)
+
+    def W16(self, name):
+        return self.store.layout.phys(self.store.shadow, name)
+
+    def buf(self, name):
+        return self.store.buffers[name]
+
+    def run_forward(self, stream=None):
+        s = L.stream() if stream is None else stream
+        for f in self.fwd:
+            f(s)
+
+    def run_backward(self, stream=None):
+        s = L.stream() if stream is None else stream
+        for f in self.bwd:
+            f(s)
+
+    # ---- ops ------------------------------------------------------------------------------------------
+    def stem(self, wname, bname, Cout, k):
+        op = _Stem(self, wname, bname, Cout, k)
+        self.ops.append(op)
+        return op.y
+
+    def conv(self, x, wname, bname, Cout, k, stride, pad):
+        op = _Conv(self, x, wname, bname, Cout, k, stride, pad, transposed=False)
+        self.ops.append(op)
+        return op.y
+
+    def deconv(self, x, wname, Cout, k=4, stride=2, pad=1):
+        op = _Conv(self, x, wname, None, Cout, k, stride, pad, transposed=True)
+        self.ops.append(op)
+        return op.y
+
+    def bn_act(self, y, prefix, relu, res=None, res_y=None, res_prefix=None):
+        op = _BNAct(self, y, prefix, relu, res, res_y, res_prefix)
+        self.ops.append(op)
+        return op.out
+
+    def add(self, a, b, c=None):
+        op = _Add(self, a, b, c)
+        self.ops.append(op)
+        return op.out
+
+    def maxpool(self, x, k, s, p):
+        op = _MaxPool(self, x, k, s, p)
+        self.ops.append(op)
+        return op.out
+
+    def upsample_add(self, up, low):
+        op = _UpAdd(self, up, low)
+        self.ops.append(op)
+        return op.out
+
+    def head(self, x, gname):
+        op = _Head(self, x, gname)
+        self.ops.append(op)
+        return op
+
+    # ---- networks -------------------------------------------------------------------------------------
+    def _build_resnet(self, layers):
+        kind, counts = RESNET_SPEC[layers]
+        exp = 1 if kind == "basic" else 4
+        y0 = self.stem("pre.0.weight", None, 64, 5)
+        a0 = self.bn_act(y0, "pre.1", True)
+        c = self.maxpool(a0, 3, 2, 1)
+        inpl = 64
+        for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], counts), start=1):
+            for bi in range(nblk):
+                p = f"layer{li}.{bi}"
+                stride = 2 if (li > 1 and bi == 0) else 1
+                has_ds = bi == 0 and (stride != 1 or inpl != planes * exp)
+                if kind == "basic":
+                    o = self.bn_act(self.conv(c, p + ".conv1.weight", None, planes, 3, stride, 1), p + ".bn1", True)
+                    y_last = self.conv(o, p + ".conv2.weight", None, planes, 3, 1, 1)
+                    last_bn = p + ".bn2"
+                else:
+                    o = self.bn_act(self.conv(c, p + ".conv1.weight", None, planes, 1, 1, 0), p + ".bn1", True)
+                    o = self.bn_act(self.conv(o, p + ".conv2.weight", None, planes, 3, stride, 1), p + ".bn2", True)
+                    y_last = self.conv(o, p + ".conv3.weight", None, planes * 4, 1, 1, 0)
+                    last_bn = p + ".bn3"
+                if has_ds:
+                    yd = self.conv(c, p + ".downsample.0.weight", None, planes * exp, 1, stride, 0)
+                    c = self.bn_act(y_last, last_bn, True, res_y=yd, res_prefix=p + ".downsample.1")
+                else:
+                    c = self.bn_act(y_last, last_bn, True, res=c)
+                inpl = planes * exp
+        for i in range(4 - int(math.log(self.ds, 2))):
+            c = self.bn_act(self.deconv(c, f"deconv_layers.{3 * i}.weight", 256), f"deconv_layers.{3 * i + 1}", True)
+        self.heads = [self.head(c, "final")]
+
+    def _hg_conv(self, x, p, co, k):
+        return self.conv(x, p + ".conv.weight", p + ".conv.bias", co, k, 1, (k - 1) // 2)
+
+    def _residual(self, x, p, co):
+        ci = x.C
+        o = self._hg_conv(self.bn_act(x, p + ".bn1", True), p + ".conv1", co // 2, 1)
+        o = self._hg_conv(self.bn_act(o, p + ".bn2", True), p + ".conv2", co // 2, 3)
+        o = self._hg_conv(self.bn_act(o, p + ".bn3", True), p + ".conv3", co, 1)
+        res = self._hg_conv(x, p + ".skip_layer", co, 1) if ci != co else x
+        return self.add(o, res)
+
+    def _hourglass(self, x, p, n):
+        up1 = self._residual(x, p + ".up1", x.C)
+        low1 = self._residual(self.maxpool(x, 2, 2, 0), p + ".low1", x.C)
+        low2 = self._hourglass(low1, p + ".low2", n - 1) if n > 1 else self._residual(low1, p + ".low2", x.C)
+        low3 = self._residual(low2, p + ".low3", x.C)
+        return self.upsample_add(up1, low3)
+
+    def _build_hourglass(self, nstack):
+        y0 = self.stem("pre.0.conv.weight", "pre.0.conv.bias", 64, 5)
+        c = self.bn_act(y0, "pre.0.bn", True)
+        c = self._residual(c, "pre.1", 128)
+        c = self.maxpool(c, 2, 2, 0)
+        c = self._residual(c, "pre.3", 256)
+        c = self._residual(c, "pre.4", 256)
+        self.heads = []
+        for i in range(nstack):
+            hg = self._hourglass(c, f"hgs.{i}.0", 4)
+            f = self._residual(hg, f"features.{i}.0", 256)
+            f = self.bn_act(self._hg_conv(f, f"features.{i}.1", 256, 1), f"features.{i}.1.bn", True)
+            hd = self.head(f, f"outs.{i}")
+            self.heads.append(hd)
+            if i < nstack - 1:
+                mp = self.conv(hd.pred_nhwc(), f"merge_preds.{i}.conv.conv.weight", f"merge_preds.{i}.conv.conv.bias", 256, 1, 1, 0)
+                mf = self._hg_conv(f, f"merge_features.{i}.conv", 256, 1)
+                c = self.add(c, mp, mf)
+
+
+def _contribute(plan, act, emit):
+    """Route one gradient contribution into act.grad(): emit(dst_tensor, accumulate: bool)."""
+    g = act.grad()
+    emit(g, act.gw)
+    act.gw = True
+
+
+class _Op:
+    def plan_bwd(self):
+        raise NotImplementedError
+
+
+class _Stem(_Op):
+    """1-channel k x k stem conv (resnet_deconv.py:32 / hourglass.py:112)."""
+
+    def __init__(self, plan, wname, bname, Cout, k):
+        self.plan, self.wname, self.bname, self.k = plan, wname, bname, k
+        B, H = plan.B, plan.H
+        self.y = Act(plan, B, H, H, Cout)
+        w = plan.P(wname)        # physical [k][k][Cout][1] == [k*k][Cout]
+        b = plan.P(bname) if bname else None
+        plan.call(plan.fwd, "awr_stem_conv", plan.img, w, b, self.y.t, plan.dt, B, H, H, Cout, k)
+
+    def plan_bwd(self):
+        pl = self.plan
+        if not self.y.gw:
+            return
+        pl.call(pl.bwd, "awr_stem_wgrad", pl.img, self.y.grad(), pl.G(self.wname), pl.G(self.bname) if self.bname else None,
+                pl.dt, pl.B, pl.H, pl.H, self.y.C, self.k)
+
+
+class _Conv(_Op):
+    """Conv2d / ConvTranspose2d on NHWC activations; output is the raw (pre-BN) tensor."""
+
+    def __init__(self, plan, x, wname, bname, Cout, k, stride, pad, transposed):
+        self.plan, self.x, self.wname, self.bname = plan, x, wname, bname
+        self.k, self.stride, self.pad, self.transposed, self.Cout = k, stride, pad, transposed, Cout
+        self.Cin = x.C
+        if transposed:
+            Ho, Wo = (x.H - 1) * stride - 2 * pad + k, (x.W - 1) * stride - 2 * pad + k
+        else:
+            Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
+        self.y = Act(plan, x.N, Ho, Wo, Cout)
+        self.want_stats = None                   # BNState set by the following bn_act (stats over this output)
+        self._emit_fwd()
+
+    def _emit_fwd(self):
+        pl, x, y = self.plan, self.x, self.y
+        b = pl.P(self.bname) if self.bname else None
+        pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(self.wname), b, y.t, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
+                self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0)
+
+    def plan_bwd(self):
+        pl, x, y = self.plan, self.x, self.y
+        if not y.gw:
+            return
+        dy = y.grad()
+        gW = pl.G(self.wname)
+        # weight gradient
+        if not self.transposed:
+            pl.call(pl.bwd, "awr_conv_wgrad_simt", dy, x.t, gW, pl.dt, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
+                    self.stride, self.pad, self.Cin, 1, self.Cout * self.Cin)
+        else:
+            pl.call(pl.bwd, "awr_conv_wgrad_simt", x.t, dy, gW, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
+                    self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin)
+        if self.bname:
+            pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
+        # data gradient
+        if True:
+            w = pl.P(self.wname)
+
+            def emit(dst, acc):
+                pl.call(pl.bwd, "awr_conv_simt", dy, w, None, dst, pl.dt, y.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
+                        self.stride, self.pad, int(not self.transposed), self.Cin, 1, self.Cout * self.Cin, 0, 0, int(acc))
+            _contribute(pl, x, emit)
+
+
+class _BNAct(_Op):
+    """out = act( BN(y) [+ res | + BN_res(res_y)] )   -- BatchNorm2d(+ReLU)(+residual) of both backbones."""
+
+    def __init__(self, plan, y, prefix, relu, res, res_y, res_prefix):
+        self.plan, self.y, self.prefix, self.relu, self.res, self.res_y, self.res_prefix = plan, y, prefix, relu, res, res_y, res_prefix
+        self.bn = BNState(plan, prefix, y.C)
+        self.bn_res = BNState(plan, res_prefix, y.C) if res_y is not None else None
+        self.out = Act(plan, y.N, y.H, y.W, y.C)
+        self._emit_stats(y, self.bn)
+        if res_y is not None:
+            self._emit_stats(res_y, self.bn_res)
+        pl = plan
+        pl.call(pl.fwd, "awr_affine_act", y.t, self.bn.ss, (res.t if res is not None else (res_y.t if res_y is not None else None)),
+                (self.bn_res.ss if self.bn_res else None), self.out.t, pl.dt, y.M, y.C, int(relu))
+
+    def _emit_stats(self, y, bn):
+        pl = self.plan
+        p = bn.prefix
+        if pl.training:
+            pl.call(pl.fwd, "awr_channel_stats", y.t, pl.dt, y.M, y.C, bn.sums, 1)
+        pl.call(pl.fwd, "awr_bn_finalize", bn.sums if pl.training else None, y.M, pl.P(p + ".weight"), pl.P(p + ".bias"),
+                pl.buf(p + ".running_mean"), pl.buf(p + ".running_var"), pl.buf(p + ".num_batches_tracked") if pl.training else None,
+                bn.ss, bn.mi, y.C, BN_MOMENTUM, BN_EPS, int(pl.training))
+
+    def plan_bwd(self):
+        pl, y, out = self.plan, self.y, self.out
+        if not out.gw:
+            return
+        dout = out.grad()
+        act = out.t if self.relu else None
+        p = self.prefix
+        pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, y.t, self.bn.mi, pl.dt, y.M, y.C, self.bn.dsums)
+        dy = y.grad()
+        dy_add = dy if y.gw else None
+        dres = dres_add = None
+        if self.res is not None:
+            dres = self.res.grad()
+            dres_add = dres if self.res.gw else None
+            self.res.gw = True
+        pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, y.t, self.bn.mi, self.bn.dsums, pl.P(p + ".weight"), dy, dy_add, dres, dres_add,
+                pl.G(p + ".weight"), pl.G(p + ".bias"), pl.dt, y.M, y.C, 1)
+        y.gw = True
+        if self.res_y is not None:
+            ry, rp = self.res_y, self.res_prefix
+            pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, ry.t, self.bn_res.mi, pl.dt, ry.M, ry.C, self.bn_res.dsums)
+            dry = ry.grad()
+            pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, ry.t, self.bn_res.mi, self.bn_res.dsums, pl.P(rp + ".weight"), dry,
+                    dry if ry.gw else None, None, None, pl.G(rp + ".weight"), pl.G(rp + ".bias"), pl.dt, ry.M, ry.C, 1)
+            ry.gw = True
+
+
+class _Add(_Op):
+    """out = a + b (+ c)   (hourglass.py:58, :163)"""
+
+    def __init__(self, plan, a, b, c=None):
+        self.plan, self.ins = plan, [a, b] + ([c] if c is not None else [])
+        self.out = Act(plan, a.N, a.H, a.W, a.C)
+        pl = plan
+        pl.call(pl.fwd, "awr_affine_act", a.t, None, b.t, None, self.out.t, pl.dt, a.M, a.C, 0)
+        if c is not None:
+            pl.call(pl.fwd, "awr_affine_act", self.out.t, None, c.t, None, self.out.t, pl.dt, a.M, a.C, 0)
+
+    def plan_bwd(self):
+        pl, out = self.plan, self.out
+        if not out.gw:
+            return
+        dout = out.grad()
+        n = out.M * out.C
+        for x in self.ins:
+            def emit(dst, acc, x=x):
+                pl.call(pl.bwd, "awr_relu_bwd", dout, None, dst if acc else None, dst, pl.dt, n)
+            _contribute(pl, x, emit)
+
+
+class _MaxPool(_Op):
+    def __init__(self, plan, x, k, s, p):
+        self.plan, self.x, self.k, self.s, self.p = plan, x, k, s, p
+        Ho, Wo = (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1
+        self.out = Act(plan, x.N, Ho, Wo, x.C)
+        self.idx = torch.empty(x.N, Ho, Wo, x.C, dtype=torch.uint8, device=plan.device) if plan.training else None
+        plan.call(plan.fwd, "awr_maxpool_fwd", x.t, self.out.t, self.idx, plan.dt, x.N, x.H, x.W, x.C, k, s, p)
+
+    def plan_bwd(self):
+        pl, x, out = self.plan, self.x, self.out
+        if not out.gw:
+            return
+
+        def emit(dst, acc):
+            pl.call(pl.bwd, "awr_maxpool_bwd", out.grad(), self.idx, dst, pl.dt, x.N, x.H, x.W, x.C, self.k, self.s, self.p, int(acc))
+        _contribute(pl, x, emit)
+
+
+class _UpAdd(_Op):
+    """out = up + nearest_x2(low)   (hourglass.py:87-88)"""
+
+    def __init__(self, plan, up, low):
+        self.plan, self.up, self.low = plan, up, low
+        self.out = Act(plan, up.N, up.H, up.W, up.C)
+        plan.call(plan.fwd, "awr_upsample2_add", up.t, low.t, self.out.t, plan.dt, up.N, up.H, up.W, up.C)
+
+    def plan_bwd(self):
+        pl, out = self.plan, self.out
+        if not out.gw:
+            return
+        dout = out.grad()
+        n = out.M * out.C
+
+        def emit_up(dst, acc):
+            pl.call(pl.bwd, "awr_relu_bwd", dout, None, dst if acc else None, dst, pl.dt, n)
+        _contribute(pl, self.up, emit_up)
+
+        def emit_low(dst, acc):
+            pl.call(pl.bwd, "awr_upsample2_bwd", dout, dst, pl.dt, out.N, out.H, out.W, out.C, int(acc))
+        _contribute(pl, self.low, emit_low)
+
+
+class _Head(_Op):
+    """final1 || final2 (resnet_deconv.py:52-53,133-136) / outs_1 || outs_2 (hourglass.py:135-136,153-157):
+    one 1x1 GEMM with N = 4J (padded to 64) writing the (B,4J,F,F) fp32 NCHW volume the AWR head consumes."""
+
+    def __init__(self, plan, x, gname):
+        self.plan, self.x, self.gname = plan, x, gname
+        J = plan.J
+        self.pred = torch.empty(x.N, 4 * J, x.H, x.W, dtype=torch.float32, device=plan.device)
+        self.dpred = torch.zeros_like(self.pred) if plan.training else None   # written by the head/loss backward (or autograd)
+        self._nhwc = None
+        pl = plan
+        pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(gname + ".weight"), pl.P(gname + ".bias"), self.pred, pl.dt, x.N, x.H, x.W, x.C,
+                x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0)
+
+    def pred_nhwc(self):
+        """Prediction volume as a 64-channel NHWC activation (input of merge_preds in stacked hourglasses)."""
+        if self._nhwc is None:
+            pl, x = self.plan, self.x
+            self._nhwc = Act(pl, x.N, x.H, x.W, 64)
+            pl.call(pl.fwd, "awr_nchw_to_nhwc", self.pred, self._nhwc.t, pl.dt, x.N, 4 * pl.J, 64, x.H * x.W)
+        return self._nhwc
+
+    def plan_bwd(self):
+        pl, x = self.plan, self.x
+        J = pl.J
+        P = x.H * x.W
+        has_direct = self.dpred is not None
+        has_nhwc = self._nhwc is not None and self._nhwc.gw
+        if not (has_direct or has_nhwc):
+            return
+        if self._nhwc is None:
+            self._nhwc = Act(pl, x.N, x.H, x.W, 64)
+        d = self._nhwc.grad()
+        if has_direct:
+            if has_nhwc:
+                tmp = torch.empty_like(d)
+                pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, tmp, pl.dt, x.N, 4 * J, 64, P)
+                pl.call(pl.bwd, "awr_relu_bwd", tmp, None, d, d, pl.dt, d.numel())
+            else:
+                pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, d, pl.dt, x.N, 4 * J, 64, P)
+        g = self.gname
+        pl.call(pl.bwd, "awr_conv_wgrad_simt", d, x.t, pl.G(g + ".weight"), pl.dt, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1,
+                64 * x.C)
+        pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, 64, pl.G(g + ".bias"), 0)
+
+        def emit(dst, acc):
+            pl.call(pl.bwd, "awr_conv_simt", d, pl.P(g + ".weight"), None, dst, pl.dt, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, 0,
+                    x.C, 1, 64 * x.C, 0, 0, int(acc))
+        _contribute(pl, x, emit)

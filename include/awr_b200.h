@@ -57,6 +57,84 @@ int awr_huber_fwd(const float* x, const float* y, long long n, float* ws, float*
 /* d/dx of the above times *grad_out (device scalar, NULL == 1). */
 int awr_huber_bwd(const float* x, const float* y, long long n, const float* grad_out, float* dx, void* stream);
 
+/* ---- NHWC elementwise / normalisation kernels (storage dtype: AWR_DTYPE_F32 or AWR_DTYPE_BF16) ---------------
+ * Internal activation layout is NHWC (M = N*H*W pixels x C channels, C a power of two in [64,2048] for the
+ * per-channel reductions).  These replace nn.BatchNorm2d / nn.ReLU / residual adds / nn.MaxPool2d / nn.Upsample
+ * of model/resnet_deconv.py:31-36,145-215 and model/hourglass.py:28-88. */
+
+/* sums[0:C] += sum_m x[m,c];  with_sq: sums[C:2C] += sum_m x[m,c]^2   (sums fp32, caller zero-fills) */
+int awr_channel_stats(const void* x, int dtype, long long M, int C, float* sums, int with_sq, void* stream);
+
+/* BatchNorm2d statistics -> per-channel affine.  training: batch stats from sums/count, running stats updated with
+ * `momentum` (unbiased var), *num_batches_tracked += 1;  eval: running stats.  scale_shift[2C]; mean_invstd[2C] or NULL. */
+int awr_bn_finalize(const float* sums, long long count, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_invstd, int C,
+                    float momentum, float eps, int training, void* stream);
+
+/* out = act( ss(y) + res_ss(res) ),  ss(v)[c] = v*scale[c] + shift[c]; scale_shift / res / res_scale_shift may be NULL. */
+int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
+                   long long M, int C, int relu, void* stream);
+
+/* BN backward pass 1: dz = dout*(act_out>0) (act_out NULL: no ReLU); dsums[0:C]+=sum dz, dsums[C:2C]+=sum dz*yhat */
+int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, int dtype, long long M, int C,
+                      float* dsums, void* stream);
+/* BN backward pass 2: dy = bn_grad [+ dy_addend]; optional dres = dz [+ dres_addend] (addends may alias their outputs);
+ * dgamma/dbeta (NULL to skip) written or accumulated. */
+int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* dsums,
+                     const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
+                     float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream);
+
+/* dx = dout*(act_out>0) [+ addend]   (act_out / addend may be NULL); n elements, n % 8 == 0 */
+int awr_relu_bwd(const void* dout, const void* act_out, const void* addend, void* dx, int dtype, long long n, void* stream);
+
+/* MaxPool2d(k,s,p) NHWC; idx (uint8 per output element, arg-max tap, first max in scan order) may be NULL in fwd. */
+int awr_maxpool_fwd(const void* x, void* out, unsigned char* idx, int dtype, int N, int H, int W, int C, int k, int s, int p,
+                    void* stream);
+int awr_maxpool_bwd(const void* dout, const unsigned char* idx, void* dx, int dtype, int N, int H, int W, int C, int k, int s, int p,
+                    int accumulate, void* stream);
+
+/* out = up + nearest_upsample_x2(low)  (hourglass.py:87-88); H,W are the fine (output) size.  bwd: dlow = 2x2 block sums. */
+int awr_upsample2_add(const void* up, const void* low, void* out, int dtype, int N, int H, int W, int C, void* stream);
+int awr_upsample2_bwd(const void* dout, void* dlow, int dtype, int N, int H, int W, int C, int accumulate, void* stream);
+
+/* NCHW fp32 (N,Csrc,P) <-> NHWC dtype (N,P,C): to_nhwc zero-pads channels up to Cdst; to_nchw keeps the first Cdst. */
+int awr_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int Csrc, int Cdst, int P, void* stream);
+int awr_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, int Csrc, int Cdst, int P, void* stream);
+
+/* torch.optim.Adam (train.py:67) fused over a flat fp32 buffer; g is multiplied by grad_scale (1/world_size under DP);
+ * bf16_shadow (or NULL) receives the rounded parameters.  step_dev: device float holding the 1-based step count. */
+int awr_adam_flat(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* step_dev, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+int awr_adam_tick(float* step_dev, void* stream);
+int awr_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+
+/* ---- convolutions, CUDA-core fp32-accumulate path (fp32 precision mode; also the 1-channel stem) --------------
+ * Activations NHWC of `dtype`; weights fp32 in the physical order [kh][kw][Cout][Cin] (the canonical OIHW
+ * nn.Parameter is a permuted view of it; ConvTranspose2d IOHW likewise).  Replaces nn.Conv2d / nn.ConvTranspose2d
+ * forward + autograd (resnet_deconv.py:31-32,78-86,141-142,182-188; hourglass.py:10). */
+
+/* Generic gather convolution  out[m,n] = sum_{tap,k} in[gather(m,tap),k] * w[tap*w_tap + k*w_sk + n*w_sn] (+bias[n]).
+ *   transposed=0: input pixel = out*stride - pad + tap        (Conv2d fprop; ConvTranspose2d dgrad)
+ *   transposed=1: input pixel = (out + pad - tap)/stride      (ConvTranspose2d fprop; Conv2d dgrad)
+ *   fprop contracts Cin (w_sk=1, w_sn=Cin); dgrad contracts Cout (w_sk=Cin, w_sn=1).
+ *   out_mode 0: NHWC `dtype` (accumulate=1 adds into out); out_mode 1: NCHW fp32, first n_valid channels. */
+int awr_conv_simt(const void* in, const float* w, const float* bias, void* out, int dtype, int N, int Hi, int Wi, int Ck, int Ho,
+                  int Wo, int Cn, int R, int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode,
+                  int n_valid, int accumulate, void* stream);
+
+/* Weight gradient  dW[tap*w_tap + i*s_p + j*s_g] += sum_q pointwise[q,i] * gathered[q*stride - pad + tap, j]
+ * (q over the coarse grid N x Hc x Wc).  Conv2d: pointwise=dy, gathered=x, s_p=Cin, s_g=1.
+ * ConvTranspose2d: pointwise=x, gathered=dy, s_p=1, s_g=Cin.  dW fp32, caller zero-fills. */
+int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, int dtype, int N, int Hc, int Wc, int Cp, int Hf, int Wf,
+                        int Cg, int R, int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
+
+/* 1-channel k x k stride-1 'same' stem convolution: x (N,H,W) fp32, w [k*k][Cout] fp32, bias or NULL -> y NHWC. */
+int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout, int k,
+                  void* stream);
+/* dW[k*k][Cout] += ..., dbias[Cout] += ... (dbias may be NULL); caller zero-fills. */
+int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int dtype, int N, int H, int W, int Cout, int k,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,8 +104,20 @@ def backbone_case(net, J, ds, B, H, seed, head_std, ks, train_step):
     return case
 
 
+def schemas():
+    out = {}
+    for name, ctor in [("resnet_18_ds2", lambda: get_deconv_net(18, 14, 2)), ("resnet_50_ds2", lambda: get_deconv_net(50, 14, 2)),
+                       ("resnet_18_ds4", lambda: get_deconv_net(18, 14, 4)), ("resnet_18_ds1_J21", lambda: get_deconv_net(18, 21, 1)),
+                       ("hourglass_1", lambda: PoseNet("hourglass_1", 14)), ("hourglass_2", lambda: PoseNet("hourglass_2", 14))]:
+        m = ctor()
+        out[name] = dict(state=[(k, tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()],
+                         params=[k for k, _ in m.named_parameters()])
+    return out
+
+
 def main():
     torch.manual_seed(0)
+    torch.save(schemas(), os.path.join(HERE, "schemas.pt"))
     torch.save(head_cases(), os.path.join(HERE, "head_cases.pt"))
     cases = [
         # C1: ResNet18 B=1 fp32 forward; peaked head so the softmax is not vacuous

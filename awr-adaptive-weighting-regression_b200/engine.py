@@ -224,6 +224,7 @@ class Plan:
         self.dt = L.F32 if precision == "fp32" else L.BF16
         self.lib = L.lib()
         self.fwd, self.bwd = [], []
+        self.fwd_meta, self.bwd_meta = [], []     # per launch: (kernel entry point, algorithmic flops, algorithmic bytes)
         self._arena_total = 0
         self.arena_buf = torch.zeros(1 << 22, dtype=torch.float32, device=device)    # zeroed at the start of every step
         self.ops = []
@@ -250,8 +251,9 @@ class Plan:
             raise RuntimeError("plan arena exhausted")
         return self.arena_buf[off: off + n]
 
-    def call(self, lst, fn, *args):
-        """Bind a C-ABI launch. Tensor-like args are resolved to pointers now (buffers are static)."""
+    def call(self, lst, fn, *args, flops=0, nbytes=0, tag=None):
+        """Bind a C-ABI launch. Tensor-like args are resolved to pointers now (buffers are static).
+        flops / nbytes: algorithmic work of this launch (for the roofline report); tag: kernel class label."""
         cargs = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
         name = fn
         f = getattr(self.lib, fn)
@@ -261,6 +263,7 @@ class Plan:
             if rc != 0:
                 L.check(rc, name)
         lst.append(run)
+        (self.fwd_meta if lst is self.fwd else self.bwd_meta).append((tag or fn, flops, nbytes))
 
     def P(self, name):
         return self.store.layout.phys(self.store.params, name)
@@ -439,13 +442,15 @@ class _Conv(_Op):
             Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
         self.y = Act(plan, x.N, Ho, Wo, Cout)
         self.want_stats = None                   # BNState set by the following bn_act (stats over this output)
+        coarse = x.M if transposed else self.y.M   # algorithmic GEMM work: 2 * Cin*Cout*k*k per pixel of the coarse side
+        self.flops = 2 * coarse * self.Cin * Cout * k * k
         self._emit_fwd()
 
     def _emit_fwd(self):
         pl, x, y = self.plan, self.x, self.y
         b = pl.P(self.bname) if self.bname else None
         pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(self.wname), b, y.t, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
-                self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0)
+                self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0, flops=self.flops, tag="conv_fprop")
 
     def plan_bwd(self):
         pl, x, y = self.plan, self.x, self.y
@@ -456,10 +461,10 @@ class _Conv(_Op):
         # weight gradient
         if not self.transposed:
             pl.call(pl.bwd, "awr_conv_wgrad_simt", dy, x.t, gW, pl.dt, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
-                    self.stride, self.pad, self.Cin, 1, self.Cout * self.Cin)
+                    self.stride, self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
         else:
             pl.call(pl.bwd, "awr_conv_wgrad_simt", x.t, dy, gW, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
-                    self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin)
+                    self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
         if self.bname:
             pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
         # data gradient
@@ -468,7 +473,8 @@ class _Conv(_Op):
 
             def emit(dst, acc):
                 pl.call(pl.bwd, "awr_conv_simt", dy, w, None, dst, pl.dt, y.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
-                        self.stride, self.pad, int(not self.transposed), self.Cin, 1, self.Cout * self.Cin, 0, 0, int(acc))
+                        self.stride, self.pad, int(not self.transposed), self.Cin, 1, self.Cout * self.Cin, 0, 0, int(acc),
+                        flops=self.flops, tag="conv_dgrad")
             _contribute(pl, x, emit)
 
 
@@ -600,7 +606,7 @@ class _Head(_Op):
         self._nhwc = None
         pl = plan
         pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(gname + ".weight"), pl.P(gname + ".bias"), self.pred, pl.dt, x.N, x.H, x.W, x.C,
-                x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0)
+                x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
 
     def pred_nhwc(self):
         """Prediction volume as a 64-channel NHWC activation (input of merge_preds in stacked hourglasses)."""
@@ -630,10 +636,10 @@ class _Head(_Op):
                 pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, d, pl.dt, x.N, 4 * J, 64, P)
         g = self.gname
         pl.call(pl.bwd, "awr_conv_wgrad_simt", d, x.t, pl.G(g + ".weight"), pl.dt, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1,
-                64 * x.C)
+                64 * x.C, flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
         pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, 64, pl.G(g + ".bias"), 0)
 
         def emit(dst, acc):
             pl.call(pl.bwd, "awr_conv_simt", d, pl.P(g + ".weight"), None, dst, pl.dt, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, 0,
-                    x.C, 1, 64 * x.C, 0, 0, int(acc))
+                    x.C, 1, 64 * x.C, 0, 0, int(acc), flops=2 * x.M * x.C * 4 * J, tag="conv_dgrad")
         _contribute(pl, x, emit)

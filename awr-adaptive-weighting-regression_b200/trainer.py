@@ -1,0 +1,150 @@
+"""Fused training step of the AWR hot path (the loop body of the reference's train.py:107-131) on libawr_b200.so.
+
+    H2D(img, jt_uvd_gt) -> backbone fwd -> fused head+loss fwd -> fused head+loss bwd -> backbone bwd
+        -> [NCCL all-reduce of the flat gradient buffer] -> fused Adam
+
+The step is a fixed launch sequence over static buffers (engine.Plan), captured once into CUDA graphs:
+`graph_fb` (zero scratch, forward, head, backward) and `graph_opt` (Adam); the data-parallel all-reduce
+runs between them on the same stream through torch.distributed (NCCL over NVLink).  GT volumes, the
+coordinate grid and the loss temporaries of the reference are never materialised (csrc/head.cu).
+
+Semantics kept from train.py: loss = coord_weight*SmoothL1(uvd, jt) + dense_weight*SmoothL1(pred, joint2offset(jt))
+(:119-120); for 'hourglass_N' only the last stack is supervised (:116-121 overwrite `loss`); Adam(lr, betas
+(0.9,0.999), eps 1e-8, weight_decay) (:67); BN statistics are per replica (the reference has no SyncBN).
+"""
+import torch
+
+from . import _lib as L
+from .modules import AWRBackbone
+
+
+class FusedTrainer:
+    def __init__(self, module: AWRBackbone, batch_size, img_size, kernel_size, coord_weight=1.0, dense_weight=1.0, lr=1e-3,
+                 betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1, use_graph=True, process_group=None):
+        if not isinstance(module, AWRBackbone):
+            raise TypeError("FusedTrainer drives awr_b200 backbones (get_deconv_net / PoseNet)")
+        self.module = module
+        module.train()
+        self.B, self.H = int(batch_size), int(img_size)
+        self.ks, self.cw, self.dw = float(kernel_size), float(coord_weight), float(dense_weight)
+        self.lr, self.betas, self.eps, self.wd = float(lr), betas, float(eps), float(weight_decay)
+        self.world, self.pg = int(world_size), process_group
+        self.store = module.store()
+        self.plan = module.plan(self.B, self.H, True)
+        dev = self.store.device
+        self.device = dev
+        self.lib = L.lib()
+        J = module._J
+        self.J = J
+        self.head = self.plan.heads[-1]
+        self.F = self.head.pred.shape[-1]
+        n = self.store.params.numel()
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.jt = torch.empty(self.B, J, 3, dtype=torch.float32, device=dev)
+        self.uvd = torch.empty(self.B, J, 3, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.ws = torch.zeros(4 * self.B * J + 4, dtype=torch.float32, device=dev)
+        self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.steps_done = 0
+        self.use_graph = use_graph
+        self.graph_fb = self.graph_opt = None
+        if self.plan.precision == "bf16":
+            self.store.refresh_shadow()
+        # launches of OUR kernels per step (memsets / NCCL not counted)
+        self.launches_per_step = len(self.plan.fwd) + len(self.plan.bwd) + 2 + 2
+
+    # ---- launch sequences -------------------------------------------------------------------------------
+    def _fwd_bwd(self):
+        pl, st, s = self.plan, self.store, L.stream()
+        pl.arena_buf.zero_()
+        st.grads.zero_()
+        for h in pl.heads[:-1]:
+            h.dpred.zero_()
+        pl.run_forward(s)
+        hd = self.head
+        L.check(self.lib.awr_head_fwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), self.uvd.data_ptr(),
+                                      self.loss.data_ptr(), self.ws.data_ptr(), self.B, self.J, self.F, self.H, self.ks, s), "awr_head_fwd")
+        L.check(self.lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), self.uvd.data_ptr(),
+                                      self.ws.data_ptr(), None, None, hd.dpred.data_ptr(), self.B, self.J, self.F, self.H, self.ks,
+                                      self.cw, self.dw, s), "awr_head_bwd")
+        pl.run_backward(s)
+
+    def _opt(self):
+        st, s = self.store, L.stream()
+        L.check(self.lib.awr_adam_tick(self.step_dev.data_ptr(), s), "awr_adam_tick")
+        shadow = st.shadow.data_ptr() if self.plan.precision == "bf16" else None
+        L.check(self.lib.awr_adam_flat(st.params.data_ptr(), st.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), shadow,
+                                       st.params.numel(), self.step_dev.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                       self.wd, 1.0 / self.world, s), "awr_adam_flat")
+
+    def _allreduce(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # warm-up outside capture (lazy module loads, first-touch)
+            self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self._fwd_bwd()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            self._opt()
+        # the warm-up / capture passes advanced BN running statistics but not the parameters or the Adam state
+
+    # ---- public API -------------------------------------------------------------------------------------
+    def load_batch(self, img, jt_uvd_gt):
+        """Copy one batch (host pinned or device tensors) into the static input buffers (async on the current stream)."""
+        self.plan.img.copy_(img.view(self.B, 1, self.H, self.H), non_blocking=True)
+        self.jt.copy_(jt_uvd_gt, non_blocking=True)
+
+    def run_step(self):
+        """One optimisation step on the batch currently in the static buffers; no host sync."""
+        if self.use_graph:
+            if self.graph_fb is None:
+                self._capture()
+            self.graph_fb.replay()
+            self._allreduce()
+            self.graph_opt.replay()
+        else:
+            self._fwd_bwd()
+            self._allreduce()
+            self._opt()
+        self.steps_done += 1
+
+    def train_step(self, img, jt_uvd_gt):
+        """The call a training loop makes: host (pinned) or device batch in, python floats (loss_coord, loss_dense) out.
+        Includes the H2D copies and the D2H loss read-back (train.py:109-133)."""
+        self.load_batch(img, jt_uvd_gt)
+        self.run_step()
+        self.loss_host.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host[0]), float(self.loss_host[1])
+
+    def broadcast_parameters(self, src=0):
+        """DDP-style start: every replica takes rank `src`'s parameters and BN buffers."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.store.params, src=src, group=self.pg)
+            for b in self.store.buffers.values():
+                dist.broadcast(b, src=src, group=self.pg)
+            if self.plan.precision == "bf16":
+                self.store.refresh_shadow()
+
+    def optimizer_state_dict(self):
+        """torch.optim.Adam-shaped state (train.py:165-172 saves optimizer.state_dict()) over the canonical parameters."""
+        lay, st = self.store.layout, self.store
+        state = {}
+        for i, name in enumerate(self.module._pnames):
+            state[i] = {"step": torch.tensor(float(self.steps_done)), "exp_avg": lay.view(self.m, name).clone(),
+                        "exp_avg_sq": lay.view(self.v, name).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
+                 "params": list(range(len(self.module._pnames)))}
+        return {"state": state, "param_groups": [group]}

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Headline benchmark of the AWR hot path on B200: training depth-frames/sec, device-timed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--net resnet_18] [--batch 32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one full train.py:107-131 iteration (GT volume, backbone fwd, AWR head, joint+dense SmoothL1, backward,
+[NCCL grad all-reduce], Adam) over one synthetic batch of `--batch` 128x128 depth crops per GPU, 14 joints.
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same step through FusedTrainer.train_step
+with pinned HOST buffers (H2D of the batch + D2H of the losses inside the timed region).
+`--impl reference` times the CPU port of the reference's own path (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "training depth-frames/sec (device-timed) ResNet18-AWR 128x128x14J"
+UNIT = "frames/s"
+J = 14
+H = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--net", default="resnet_18")
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU (weak scaling)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg (0 disables)")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle's restatement of train.py:107-131 on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_train_steps(net, ds, ks, batch, steps, warmup=1):
+    import torch
+    from oracle import awr_oracle as O        # checker / CPU baseline only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, n = net.split("_")
+    sd = O.resnet_deconv_init(int(n), J, ds, 1) if kind == "resnet" else O.hourglass_init(int(n), J, 1)
+    img, jt = O.synthetic_batch(batch, H, J, 0)
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()
+             if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, lc, ld, _, _, grads, new_stats = O.loss_and_grads(sd, img, jt, net, ds, ks, 1.0, 1.0)
+        with torch.no_grad():
+            for k, g in grads.items():
+                if g is not None:
+                    O.adam_step(sd[k], g, state[k][0], state[k][1], it + 1)
+            for k, v in new_stats.items():
+                sd[k] = v
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return batch * len(times) / sum(times), cores, times
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ds, ks = 2, (1.0 if a.net.startswith("resnet") else 0.4)
+    steps = max(1, min(a.steps, 4))
+    fps, cores, times = cpu_train_steps(a.net, ds, ks, a.batch, steps, warmup=min(a.warmup, 1))
+    sample = f"{steps} full train steps (after 1 warm-up) of the same workload at batch {a.batch}, fp32, torch CPU ops, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": min(a.warmup, 1), "ms_per_step": round(1e3 * sum(times) / len(times), 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, 1),
+            "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(fps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, world):
+    return {"workload": f"{a.net}-deconv AWR full train step, {H}x{H}x1 depth crops, {J} joints, batch {a.batch}/GPU",
+            "global_batch": a.batch * world, "img_size": H, "joints": J, "downsample": 2, "optimizer": "Adam lr 1e-3",
+            "parallelism": f"dp{world}"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# per-kernel-class device timing of one eager step (CUDA events on the launch stream, queue pre-filled behind a spin)
+# ---------------------------------------------------------------------------------------------------------
+def classify_step(tr, steps):
+    import torch
+    from awr_b200 import _lib as L
+    pl = tr.plan
+    agg = {}
+    for _ in range(steps):
+        evs = []
+        s = L.stream()
+        torch.cuda._sleep(int(40e6))          # ~20 ms: lets the host enqueue the whole step so events are back-to-back
+        pl.arena_buf.zero_(); tr.store.grads.zero_()
+        seq = [(f, m) for f, m in zip(pl.fwd, pl.fwd_meta)]
+        hd = tr.head
+        lib = tr.lib
+        head_f = lambda st: L.check(lib.awr_head_fwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), tr.jt.data_ptr(), tr.uvd.data_ptr(),
+                                                     tr.loss.data_ptr(), tr.ws.data_ptr(), tr.B, tr.J, tr.F, tr.H, tr.ks, st), "head_fwd")
+        head_b = lambda st: L.check(lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), tr.jt.data_ptr(), tr.uvd.data_ptr(),
+                                                     tr.ws.data_ptr(), None, None, hd.dpred.data_ptr(), tr.B, tr.J, tr.F, tr.H, tr.ks,
+                                                     tr.cw, tr.dw, st), "head_bwd")
+        P = tr.F * tr.F
+        fwd_bytes = tr.B * (4 * tr.J * P * 4 + P * 4) + tr.B * tr.J * 24
+        bwd_bytes = tr.B * (2 * 4 * tr.J * P * 4 + P * 4) + tr.B * tr.J * 24
+        seq.append((head_f, ("head_fwd", 0, fwd_bytes)))
+        seq.append((head_b, ("head_bwd", 0, bwd_bytes)))
+        seq += [(f, m) for f, m in zip(pl.bwd, pl.bwd_meta)]
+        for f, m in seq:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); f(s); e1.record()
+            evs.append((m, e0, e1))
+        tr._opt()
+        torch.cuda.synchronize()
+        for (tag, fl, nb), e0, e1 in evs:
+            a = agg.setdefault(tag, [0.0, 0, 0, 0])
+            a[0] += e0.elapsed_time(e1); a[1] += fl; a[2] += nb; a[3] += 1
+    return agg
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import awr_b200
+    from awr_b200.trainer import FusedTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a kernels; there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ds, ks = 2, (1.0 if a.net.startswith("resnet") else 0.4)
+
+    torch.manual_seed(1)
+    kind, n = a.net.split("_")
+    net = awr_b200.get_deconv_net(int(n), J, ds, precision=a.precision) if kind == "resnet" else awr_b200.PoseNet(a.net, J, precision=a.precision)
+    net = net.to(dev)
+    tr = FusedTrainer(net, a.batch, H, ks, 1.0, 1.0, lr=1e-3, world_size=world, use_graph=not a.no_graph)
+    tr.broadcast_parameters(0)
+
+    # synthetic batch, per-rank seed; a few distinct batches rotate through the e2e leg
+    g = torch.Generator().manual_seed(1000 + rank)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, H), indexing="ij")
+
+    def make_batch():
+        cx, cy = (torch.rand(a.batch, 1, 1, generator=g) - 0.5) * 0.4, (torch.rand(a.batch, 1, 1, generator=g) - 0.5) * 0.4
+        rx, ry = 0.45 + 0.3 * torch.rand(a.batch, 1, 1, generator=g), 0.45 + 0.3 * torch.rand(a.batch, 1, 1, generator=g)
+        inside = ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 < 1.0
+        depth = (0.5 * (xx - cx) + 0.3 * (yy - cy) + 0.05 * torch.randn(a.batch, H, H, generator=g)).clamp(-1.0, 0.98)
+        img = torch.where(inside, depth, torch.ones_like(depth)).unsqueeze(1).contiguous().float()
+        jt = (torch.rand(a.batch, J, 3, generator=g) - 0.5).float()
+        return img.pin_memory(), jt.pin_memory()
+
+    host_batches = [make_batch() for _ in range(4)]
+    dev_batches = [(i.to(dev), j.to(dev)) for i, j in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg (value) --------------------------------------------------------------------
+    for w in range(max(a.warmup, 3)):
+        tr.load_batch(*dev_batches[w % 4]); tr.run_step()
+    clk = Clocks(local)
+    if rank == 0:
+        clk.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(a.steps):
+        tr.load_batch(*dev_batches[k % 4])      # device->device 2 MB copy: the batch of this step, already in HBM
+        tr.run_step()
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+    losses = tr.loss.tolist()
+    value = a.batch * world * a.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg: host pinned batch -> train_step -> host losses ----------------------------------
+    for w in range(3):
+        tr.train_step(*host_batches[w % 4])
+    barrier()
+    e0.record()
+    for k in range(a.steps):
+        lc, ld = tr.train_step(*host_batches[k % 4])
+    e1.record()
+    barrier()
+    t2 = time.perf_counter()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = t.item()
+    e2e = a.batch * world * a.steps / (ms_e2e * 1e-3)
+    h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 4
+    clocks = None
+    if rank == 0:
+        clk.stop()
+        clocks = clk.summary(t0, t2)
+
+    # ---- roofline of the dominant kernels (rank 0, eager step, events around every launch) ----------------
+    roof = roof_head = None
+    classes = {}
+    if rank == 0:
+        pk = peaks()
+        agg = classify_step(tr, 3)
+        tot = sum(v[0] for v in agg.values())
+        classes = {k: {"ms_per_step": round(v[0] / 3, 4), "share": round(v[0] / tot, 4), "launches_per_step": v[3] // 3} for k, v in
+                   sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        conv = [v for k, v in agg.items() if k.startswith("conv_")]
+        cms, cfl, cn = sum(v[0] for v in conv), sum(v[1] for v in conv), sum(v[3] for v in conv)
+        ach = cfl / (cms * 1e-3) / 1e12
+        roof = {"kernel": "conv/deconv implicit-GEMM (fprop+dgrad+wgrad)", "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sust"],
+                "unit": "TFLOP/s", "frac": round(ach / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                "launches_per_step": cn // 3, "avg_launch_us": round(1e3 * cms / cn, 2), "share_of_step": round(cms / tot, 4),
+                "flops_per_step": cfl // 3}
+        hv = [agg["head_fwd"], agg["head_bwd"]]
+        hms, hb = sum(v[0] for v in hv), sum(v[2] for v in hv)
+        hach = hb / (hms * 1e-3) / 1e9
+        roof_head = {"kernel": "fused AWR head+loss (fwd, bwd)", "bound": "hbm", "achieved": round(hach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                     "frac": round(hach / pk["hbm"], 4), "traffic": None, "peak_source": pk["src"] + " (copy)",
+                     "avg_launch_us": round(1e3 * hms / 6, 2), "bytes_per_step": hb // 3, "share_of_step": round(hms / tot, 4)}
+
+    # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and a.cpu_steps > 0:
+        fps, cores, times = cpu_train_steps(a.net, ds, ks, a.batch, a.cpu_steps)
+        cpu = {"value": round(fps, 3), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{a.cpu_steps} full train steps (1 warm-up) at batch {a.batch}, fp32, oracle/awr_oracle.py on torch CPU ops"}
+
+    if rank == 0:
+        act_bytes = sum(op.y.t.numel() * op.y.t.element_size() for op in tr.plan.ops if hasattr(op, "y"))
+        cfg = workload_config(a, world)
+        cfg.update({"precision": a.precision, "l2": f"no flush needed: per-step conv outputs alone are {act_bytes / 2**20:.0f} MiB (> 126 MB L2), "
+                    "rotating 4 input batches", "cuda_graph": not a.no_graph, "e2e_api": "awr_b200.trainer.FusedTrainer.train_step(pinned host img, jt)"})
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": a.precision, "data": "synthetic", "config": cfg, "clocks": clocks,
+                "e2e": {"value": round(e2e, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                        "ms_per_step": round(ms_e2e / a.steps, 4)},
+                "gpu_launches": tr.launches_per_step * a.steps, "launches_per_step": tr.launches_per_step,
+                "roofline": roof, "roofline_head": roof_head, "kernel_classes": classes, "cpu_baseline": cpu,
+                "loss": {"coord": lc, "dense": ld}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,15 @@ int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, in
 int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int dtype, int N, int H, int W, int Cout, int k,
                    void* stream);
 
+/* ---- convolutions, tcgen05 tensor-core path (bf16 precision mode) ------------------------------------------------
+ * NHWC bf16 activations, bf16 weights (the Adam kernel's shadow copy, same physical order [kh][kw][Cout][Cin]), fp32
+ * accumulation in TMEM, operands staged by TMA (shifted boxes = implicit im2col, zero OOB fill = padding).
+ * Same argument meaning as awr_conv_simt (w strides select fprop [w_sk==1] or dgrad [w_sn==1]); Ck, Cn multiples of 64,
+ * feature-map sides powers of two <= 256, stride 1 or 2.  Returns AWR_ERR_DRIVER (-3) if the driver cannot encode a tensor map. */
+int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, int N, int Hi, int Wi, int Ck, int Ho, int Wo, int Cn, int R,
+                int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode, int n_valid, int accumulate,
+                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

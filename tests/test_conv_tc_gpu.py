@@ -1,0 +1,104 @@
+"""GPU numerics of the tcgen05 implicit-GEMM convolution kernels (through the C-ABI) vs plain PyTorch fp32 on the same
+bf16-rounded operands.  Tolerance: fp32 accumulation of bf16 products, output rounded to bf16 -> 1e-2 relative to the
+tensor's max (bf16 has 8 mantissa bits: 2^-8 = 3.9e-3 per rounding)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(t):          # (N,C,H,W) fp32 -> NHWC bf16 cuda
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def _from_nhwc(t):     # NHWC bf16 cuda -> (N,C,H,W) fp32 cpu
+    return t.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def _rb(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _conv_tc(x, w_phys, bias, out, N, Hi, Wi, Ck, Ho, Wo, Cn, k, stride, pad, transposed, w_sk, w_sn, w_tap, out_mode=0, n_valid=0, acc=0):
+    from awr_b200 import _lib as L
+    L.check(L.lib().awr_conv_tc(x.data_ptr(), w_phys.data_ptr(), None if bias is None else bias.data_ptr(), out.data_ptr(), N, Hi, Wi, Ck,
+                                Ho, Wo, Cn, k, k, stride, pad, transposed, w_sk, w_sn, w_tap, out_mode, n_valid, acc, L.stream()), "awr_conv_tc")
+    torch.cuda.synchronize()
+
+
+CONV_CASES = [  # N, Cin, Cout, H, k, stride, pad
+    (2, 64, 64, 16, 3, 1, 1),
+    (3, 128, 256, 8, 1, 1, 0),
+    (2, 64, 128, 32, 3, 2, 1),
+    (2, 64, 128, 32, 1, 2, 0),
+    (2, 128, 128, 64, 3, 1, 1),
+    (5, 256, 512, 4, 3, 1, 1),
+    (1, 64, 64, 128, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "N%d_%dto%d_H%d_k%ds%dp%d" % c)
+def test_conv2d_fprop_dgrad(case):
+    N, Ci, Co, H, k, s, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _rb(torch.randn(N, Ci, H, H, generator=g))
+    w = _rb(torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5)
+    b = torch.randn(Co, generator=g)
+    Ho = (H + 2 * pad - k) // s + 1
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv2d(xr, w, b, stride=s, padding=pad)
+    gy = _rb(torch.randn(ref.shape, generator=g))
+    ref.backward(gy)
+    w_phys = w.permute(2, 3, 0, 1).contiguous().to(torch.bfloat16).cuda()       # [kh][kw][Co][Ci]
+    y = torch.full((N, Ho, Ho, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _conv_tc(_nhwc(x), w_phys, b.cuda(), y, N, H, H, Ci, Ho, Ho, Co, k, s, pad, 0, 1, Ci, Co * Ci)
+    got = _from_nhwc(y)
+    assert (got - ref.detach()).abs().max().item() < 1e-2 * ref.abs().max().item()
+    # dgrad: dx = conv_transpose(dy, w)  -> contraction over Cout, MN-major B from the same weight buffer
+    dx = torch.full((N, H, H, Ci), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _conv_tc(_nhwc(gy), w_phys, None, dx, N, Ho, Ho, Co, H, H, Ci, k, s, pad, 1, Ci, 1, Co * Ci)
+    gdx = _from_nhwc(dx)
+    assert (gdx - xr.grad).abs().max().item() < 1e-2 * xr.grad.abs().max().item()
+    # accumulate mode adds into the existing tensor
+    _conv_tc(_nhwc(gy), w_phys, None, dx, N, Ho, Ho, Co, H, H, Ci, k, s, pad, 1, Ci, 1, Co * Ci, acc=1)
+    assert (_from_nhwc(dx) - 2 * xr.grad).abs().max().item() < 2e-2 * xr.grad.abs().max().item()
+
+
+DECONV_CASES = [(2, 128, 64, 8), (2, 512, 256, 8), (3, 256, 256, 16), (1, 64, 64, 64)]   # N, Cin, Cout, Hin  (k4 s2 p1)
+
+
+@pytest.mark.parametrize("case", DECONV_CASES, ids=lambda c: "N%d_%dto%d_H%d" % c)
+def test_conv_transpose2d_fprop_dgrad(case):
+    N, Ci, Co, H = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _rb(torch.randn(N, Ci, H, H, generator=g))
+    w = _rb(torch.randn(Ci, Co, 4, 4, generator=g) / (Ci * 4) ** 0.5)           # ConvTranspose2d IOHW
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv_transpose2d(xr, w, None, stride=2, padding=1)
+    gy = _rb(torch.randn(ref.shape, generator=g))
+    ref.backward(gy)
+    Ho = 2 * H
+    w_phys = w.permute(2, 3, 1, 0).contiguous().to(torch.bfloat16).cuda()       # [kh][kw][Co][Ci]
+    y = torch.full((N, Ho, Ho, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _conv_tc(_nhwc(x), w_phys, None, y, N, H, H, Ci, Ho, Ho, Co, 4, 2, 1, 1, 1, Ci, Co * Ci)
+    got = _from_nhwc(y)
+    assert (got - ref.detach()).abs().max().item() < 1e-2 * ref.abs().max().item()
+    dx = torch.full((N, H, H, Ci), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _conv_tc(_nhwc(gy), w_phys, None, dx, N, Ho, Ho, Co, H, H, Ci, 4, 2, 1, 0, Ci, 1, Co * Ci)
+    assert (_from_nhwc(dx) - xr.grad).abs().max().item() < 1e-2 * xr.grad.abs().max().item()
+
+
+def test_head_conv_nchw_fp32_output():
+    """1x1 conv with 64 (56 valid) output channels written as the fp32 NCHW prediction volume."""
+    N, Ci, H, nv = 2, 256, 64, 56
+    g = torch.Generator().manual_seed(7)
+    x = _rb(torch.randn(N, Ci, H, H, generator=g))
+    w = torch.zeros(64, Ci, 1, 1)
+    w[:nv] = _rb(torch.randn(nv, Ci, 1, 1, generator=g) / Ci ** 0.5)
+    b = torch.zeros(64); b[:nv] = torch.randn(nv, generator=g)
+    ref = F.conv2d(x, w[:nv], b[:nv])
+    out = torch.full((N, nv, H, H), float("nan"), dtype=torch.float32, device="cuda")
+    w_phys = w.permute(2, 3, 0, 1).contiguous().to(torch.bfloat16).cuda()
+    _conv_tc(_nhwc(x), w_phys, b.cuda(), out, N, H, H, Ci, H, H, 64, 1, 1, 0, 0, 1, Ci, 64 * Ci, out_mode=1, n_valid=nv)
+    assert (out.cpu() - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-5      # fp32 out: only accumulation-order error

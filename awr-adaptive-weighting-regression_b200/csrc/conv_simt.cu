@@ -254,6 +254,65 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   if (tg == 0 && dbias) atomicAdd(dbias + co, bsum);
 }
 
+// Register-tiled stem weight gradient (K x K taps, 1 input channel): block = one image x 8-row band, 4 thread groups x Cout=64
+// channels; each thread keeps all K*K tap accumulators for its channel and walks 8-pixel row segments so every x value
+// fetched from the smem halo tile feeds K FMAs.  One atomicAdd per (tap, channel) per block.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
+                                                               float* __restrict__ dbias, int N, int H, int W) {
+  constexpr int RB = 8, CO = 64, PADK = K / 2, XS = 8 + K - 1;
+  extern __shared__ __align__(16) float sm[];
+  const int pitch = ((W + K - 1) + 3) & ~3;
+  float* xt = sm;                                   // [(RB+K-1)][pitch]
+  float* red = sm + (RB + K - 1) * pitch;           // [4][K*K+1][CO]
+  const int n = blockIdx.x / (H / RB), h0 = (blockIdx.x % (H / RB)) * RB;
+  const int co = threadIdx.x & (CO - 1), grp = threadIdx.x >> 6;
+  const float* xi = x + (size_t)n * H * W;
+  for (int i = threadIdx.x; i < (RB + K - 1) * pitch; i += 256) {
+    const int rr = i / pitch, cc = i - rr * pitch;
+    const int hh = h0 + rr - PADK, ww = cc - PADK;
+    xt[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W && cc < W + K - 1) ? __ldg(xi + (size_t)hh * W + ww) : 0.f;
+  }
+  __syncthreads();
+  float acc[K * K];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) acc[t] = 0.f;
+  float bsum = 0.f;
+  const int octs_per_row = W / 8, octs = RB * octs_per_row;
+  for (int o = grp; o < octs; o += 4) {
+    const int rr = o / octs_per_row, c0 = (o - rr * octs_per_row) * 8;
+    const T* dyp = dy + (((size_t)n * H + h0 + rr) * W + c0) * CO + co;
+    float g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = to_f<T>(dyp[(size_t)i * CO]); bsum += g[i]; }
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const float* xr = xt + (rr + r) * pitch + c0;
+      float xs[XS];
+#pragma unroll
+      for (int i = 0; i < XS; ++i) xs[i] = xr[i];
+#pragma unroll
+      for (int s2 = 0; s2 < K; ++s2) {
+        float a = acc[r * K + s2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a = fmaf(g[i], xs[i + s2], a);
+        acc[r * K + s2] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) red[(grp * (K * K + 1) + t) * CO + co] = acc[t];
+  red[(grp * (K * K + 1) + K * K) * CO + co] = bsum;
+  __syncthreads();
+  for (int t = grp; t < K * K + 1; t += 4) {
+    float v = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < 4; ++g2) v += red[(g2 * (K * K + 1) + t) * CO + co];
+    if (t < K * K) atomicAdd(dW + t * CO + co, v);
+    else if (dbias) atomicAdd(dbias + co, v);
+  }
+}
+
 }  // namespace
 
 #define DISPATCH_T(dtype, ...)                                             \
@@ -313,6 +372,13 @@ int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int 
   AWR_HOST_CHECK((k * k + (256 / Cout) - 1) / (256 / Cout) <= 8 * 1 || true);
   // taps handled per thread = ceil(k*k / (256/Cout)) must be <= 8
   AWR_HOST_CHECK((k * k + (256 / Cout) - 1) / (256 / Cout) <= 8);
+  if (k == 5 && Cout == 64 && H % 8 == 0 && W % 8 == 0 && W <= 256) {
+    const int pitch = ((W + 4) + 3) & ~3;
+    const size_t smem = ((size_t)12 * pitch + 4 * 26 * 64) * sizeof(float);
+    DISPATCH_T(dtype, stem_wgrad_tiled_kernel<T, 5><<<N * (H / 8), 256, smem, (cudaStream_t)stream>>>(x, (const T*)dy, dW, dbias, N, H, W));
+    AWR_LAUNCH_CHECK();
+    return AWR_OK;
+  }
   DISPATCH_T(dtype, stem_wgrad_kernel<T><<<(int)((P + ppb - 1) / ppb), 256, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dW, dbias, N, H,
                                                                                                       W, Cout, k, ppb));
   AWR_LAUNCH_CHECK();

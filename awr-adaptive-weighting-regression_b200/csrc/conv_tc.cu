@@ -47,7 +47,7 @@ struct ConvTcParams {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
-               void* __restrict__ outp, const __grid_constant__ ConvTcParams p) {
+               void* __restrict__ outp, float* __restrict__ stats, const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
@@ -155,13 +155,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        if (!valid) continue;
+        if (!valid && !stats) continue;
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
         if (bias) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] += __ldg(bias + c0 + ch + i);
+        }
+        if (stats) {
+          // per-channel sum / sum of squares of the bf16-rounded outputs (what BatchNorm will normalise): 32x32 transpose-
+          // reduce over the warp's rows with 31 shuffles per quantity; lane L ends up owning channel c0+ch+L.
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float r = valid ? __bfloat162float(__float2bfloat16_rn(f[i])) : 0.f;
+            s1[i] = r; s2[i] = r * r;
+          }
+#pragma unroll
+          for (int st = 16; st > 0; st >>= 1) {
+            const bool up = (lane & st) != 0;
+#pragma unroll
+            for (int i = 0; i < st; ++i) {
+              const float k1 = up ? s1[i + st] : s1[i], d1 = up ? s1[i] : s1[i + st];
+              const float k2 = up ? s2[i + st] : s2[i], d2 = up ? s2[i] : s2[i + st];
+              s1[i] = k1 + __shfl_xor_sync(0xffffffffu, d1, st);
+              s2[i] = k2 + __shfl_xor_sync(0xffffffffu, d2, st);
+            }
+          }
+          atomicAdd(stats + c0 + ch + lane, s1[0]);
+          atomicAdd(stats + p.Cn + c0 + ch + lane, s2[0]);
+          if (!valid) continue;
         }
         if (p.out_mode == 0) {
           bf16* dst = reinterpret_cast<bf16*>(outp) + (((size_t)n * p.Ho + ho) * p.Wo + wo) * p.Cn + c0 + ch;
@@ -203,14 +227,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 extern "C" {
 
-int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, int N, int Hi, int Wi, int Ck, int Ho, int Wo, int Cn, int R,
-                int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode, int n_valid, int accumulate,
-                void* stream) {
+int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, float* stats, int N, int Hi, int Wi, int Ck, int Ho, int Wo,
+                int Cn, int R, int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode, int n_valid,
+                int accumulate, void* stream) {
   AWR_HOST_CHECK(in && w && out && N > 0 && Ck % 64 == 0 && Cn % 64 == 0 && R > 0 && S > 0 && R * S <= kMaxTaps);
   AWR_HOST_CHECK(stride == 1 || stride == 2);
   AWR_HOST_CHECK((w_sk == 1 && w_sn % 8 == 0) || (w_sn == 1 && w_sk % 8 == 0));
   AWR_HOST_CHECK(w_tap % 8 == 0 || R * S == 1);
   AWR_HOST_CHECK(out_mode == 0 || (out_mode == 1 && n_valid > 0 && n_valid <= Cn && !accumulate));
+  AWR_HOST_CHECK(stats == nullptr || (out_mode == 0 && !accumulate));
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   // coarse grid = the tensor whose pixels index GEMM rows
@@ -296,7 +321,7 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, int
   const int total_tiles = p.nclasses * p.tiles_m * p.tiles_c;
   int sms = 148;
   int grid = total_tiles < sms ? total_tiles : sms;
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, bias, out, p);
+  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, bias, out, stats, p);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -141,6 +141,85 @@ affine_act_kernel(const T* __restrict__ y, const float* __restrict__ ss, const T
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// fused BatchNorm finalize + apply (+ residual, optionally through its own BatchNorm) (+ ReLU): one launch per BN layer.
+// Every thread derives scale/shift of its 8 channels from the batch sums (training) or running statistics (eval);
+// block 0 also updates the running statistics / num_batches_tracked and saves (mean, invstd) for backward.
+// ---------------------------------------------------------------------------------------------------------
+struct BnSet {
+  const float* sums; const float* gamma; const float* beta; float* running_mean; float* running_var; long long* nbt; float* mean_invstd;
+};
+
+__device__ __forceinline__ void bn_coeffs(const BnSet& b, int c, int C, float count, float eps, int training, float& sc, float& sh, float& mean,
+                                          float& invstd, float& var) {
+  if (training) {
+    mean = b.sums[c] / count;
+    var = fmaxf(b.sums[C + c] / count - mean * mean, 0.f);
+  } else {
+    mean = b.running_mean[c];
+    var = b.running_var[c];
+  }
+  invstd = rsqrtf(var + eps);
+  sc = b.gamma[c] * invstd;
+  sh = b.beta[c] - mean * sc;
+}
+
+__device__ __forceinline__ void bn_side_effects(const BnSet& b, int C, float count, float momentum, float eps, int training) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc, sh, mean, invstd, var;
+    bn_coeffs(b, c, C, count, eps, training, sc, sh, mean, invstd, var);
+    if (b.mean_invstd) { b.mean_invstd[c] = mean; b.mean_invstd[C + c] = invstd; }
+    if (training && b.running_mean) {
+      b.running_mean[c] = (1.f - momentum) * b.running_mean[c] + momentum * mean;
+      const float unb = (count > 1.f) ? var * count / (count - 1.f) : var;
+      b.running_var[c] = (1.f - momentum) * b.running_var[c] + momentum * unb;
+    }
+  }
+  if (training && b.nbt && threadIdx.x == 0) *b.nbt += 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSet rbn, int res_has_bn, T* __restrict__ out, long long M, int C,
+              float count, float momentum, float eps, int training, int relu) {
+  const int G = C >> 3;
+  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  float sc[8], sh[8], rsc[8], rsh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float mean, invstd, var;
+    bn_coeffs(bn, c0 + k, C, count, eps, training, sc[k], sh[k], mean, invstd, var);
+    if (res_has_bn) bn_coeffs(rbn, c0 + k, C, count, eps, training, rsc[k], rsh[k], mean, invstd, var);
+  }
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    float v[8];
+    Vec8<T>::load(y + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] * sc[k] + sh[k];
+    if (res) {
+      float r[8];
+      Vec8<T>::load(res + i * 8, r);
+      if (res_has_bn) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = r[k] * rsc[k] + rsh[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    Vec8<T>::store(out + i * 8, v);
+  }
+  if (blockIdx.x == gridDim.x - 1) {      // side effects after this block's own reads of the running statistics
+    __syncthreads();
+    bn_side_effects(bn, C, count, momentum, eps, training);
+    if (res_has_bn) bn_side_effects(rbn, C, count, momentum, eps, training);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // BN backward, pass 1: dz = dout * (act_out > 0 if relu);  dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * yhat
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -483,6 +562,23 @@ int awr_bn_finalize(const float* sums, long long count, const float* gamma, cons
   bn_finalize_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, (float)count, gamma, beta, running_mean, running_var,
                                                                        num_batches_tracked, scale_shift, mean_invstd, C, momentum,
                                                                        eps, training);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_bn_act(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+               long long* num_batches_tracked, float* mean_invstd, const void* res, const float* res_sums, const float* res_gamma,
+               const float* res_beta, float* res_running_mean, float* res_running_var, long long* res_num_batches_tracked,
+               float* res_mean_invstd, void* out, int dtype, long long M, int C, float momentum, float eps, int training, int relu,
+               void* stream) {
+  AWR_HOST_CHECK(y && out && gamma && beta && M > 0 && chan_ok(C));
+  AWR_HOST_CHECK(training ? (sums != nullptr) : (running_mean && running_var));
+  const int res_has_bn = res_gamma != nullptr;
+  AWR_HOST_CHECK(!res_has_bn || (res && res_beta && (training ? (res_sums != nullptr) : (res_running_mean && res_running_var))));
+  BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
+  BnSet b{res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
+  DISPATCH_T(dtype, bn_act_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)y, a, (const T*)res, b, res_has_bn, (T*)out, M,
+                                                                                             C, (float)M, momentum, eps, training, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -9,6 +9,7 @@ Network structure follows the reference modules it replaces:
   ResNet-deconv : model/resnet_deconv.py:19-215      Hourglass : model/hourglass.py:6-165
 """
 import math
+import os
 
 import torch
 
@@ -192,6 +193,7 @@ class Act:
         self.t = torch.empty(N, H, W, C, dtype=dtype or plan.tdtype, device=plan.device)
         self.g = None
         self.gw = False          # gradient already written in the backward plan (next contribution accumulates)
+        self.stats = None        # fp32 [2C] per-channel sum / sum-of-squares filled by the producing conv's epilogue (bf16 mode)
 
     @property
     def M(self):
@@ -204,9 +206,10 @@ class Act:
 
 
 class BNState:
-    def __init__(self, plan, prefix, C):
+    def __init__(self, plan, prefix, C, sums=None):
         self.prefix, self.C = prefix, C
-        self.sums = plan.arena(2 * C)
+        self.fused_stats = sums is not None
+        self.sums = sums if sums is not None else plan.arena(2 * C)
         self.dsums = plan.arena(2 * C)
         self.ss = torch.empty(2 * C, dtype=torch.float32, device=plan.device)
         self.mi = torch.empty(2 * C, dtype=torch.float32, device=plan.device)
@@ -222,6 +225,9 @@ class Plan:
         self.precision, self.training, self.store, self.device = precision, training, store, device
         self.tdtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.dt = L.F32 if precision == "fp32" else L.BF16
+        # bf16 mode: convolutions on tcgen05 tensor cores (csrc/conv_tc.cu, wgrad_tc.cu).  AWR_B200_DEBUG_SIMT=1 keeps the bf16
+        # activations but runs the CUDA-core conv kernels with fp32 weights -- a debugging aid for isolating rounding effects.
+        self.tc = precision == "bf16" and os.environ.get("AWR_B200_DEBUG_SIMT") != "1"
         self.lib = L.lib()
         self.fwd, self.bwd = [], []
         self.fwd_meta, self.bwd_meta = [], []     # per launch: (kernel entry point, algorithmic flops, algorithmic bytes)
@@ -293,13 +299,14 @@ class Plan:
         self.ops.append(op)
         return op.y
 
-    def conv(self, x, wname, bname, Cout, k, stride, pad):
-        op = _Conv(self, x, wname, bname, Cout, k, stride, pad, transposed=False)
+    def conv(self, x, wname, bname, Cout, k, stride, pad, bn_next=True):
+        """bn_next: the output feeds a BatchNorm, so (tensor-core path, training) the conv epilogue also produces its batch statistics."""
+        op = _Conv(self, x, wname, bname, Cout, k, stride, pad, transposed=False, want_stats=bn_next)
         self.ops.append(op)
         return op.y
 
     def deconv(self, x, wname, Cout, k=4, stride=2, pad=1):
-        op = _Conv(self, x, wname, None, Cout, k, stride, pad, transposed=True)
+        op = _Conv(self, x, wname, None, Cout, k, stride, pad, transposed=True, want_stats=True)
         self.ops.append(op)
         return op.y
 
@@ -360,15 +367,15 @@ class Plan:
             c = self.bn_act(self.deconv(c, f"deconv_layers.{3 * i}.weight", 256), f"deconv_layers.{3 * i + 1}", True)
         self.heads = [self.head(c, "final")]
 
-    def _hg_conv(self, x, p, co, k):
-        return self.conv(x, p + ".conv.weight", p + ".conv.bias", co, k, 1, (k - 1) // 2)
+    def _hg_conv(self, x, p, co, k, bn_next=True):
+        return self.conv(x, p + ".conv.weight", p + ".conv.bias", co, k, 1, (k - 1) // 2, bn_next=bn_next)
 
     def _residual(self, x, p, co):
         ci = x.C
         o = self._hg_conv(self.bn_act(x, p + ".bn1", True), p + ".conv1", co // 2, 1)
         o = self._hg_conv(self.bn_act(o, p + ".bn2", True), p + ".conv2", co // 2, 3)
-        o = self._hg_conv(self.bn_act(o, p + ".bn3", True), p + ".conv3", co, 1)
-        res = self._hg_conv(x, p + ".skip_layer", co, 1) if ci != co else x
+        o = self._hg_conv(self.bn_act(o, p + ".bn3", True), p + ".conv3", co, 1, bn_next=False)
+        res = self._hg_conv(x, p + ".skip_layer", co, 1, bn_next=False) if ci != co else x
         return self.add(o, res)
 
     def _hourglass(self, x, p, n):
@@ -393,8 +400,8 @@ class Plan:
             hd = self.head(f, f"outs.{i}")
             self.heads.append(hd)
             if i < nstack - 1:
-                mp = self.conv(hd.pred_nhwc(), f"merge_preds.{i}.conv.conv.weight", f"merge_preds.{i}.conv.conv.bias", 256, 1, 1, 0)
-                mf = self._hg_conv(f, f"merge_features.{i}.conv", 256, 1)
+                mp = self.conv(hd.pred_nhwc(), f"merge_preds.{i}.conv.conv.weight", f"merge_preds.{i}.conv.conv.bias", 256, 1, 1, 0, bn_next=False)
+                mf = self._hg_conv(f, f"merge_features.{i}.conv", 256, 1, bn_next=False)
                 c = self.add(c, mp, mf)
 
 
@@ -432,7 +439,7 @@ class _Stem(_Op):
 class _Conv(_Op):
     """Conv2d / ConvTranspose2d on NHWC activations; output is the raw (pre-BN) tensor."""
 
-    def __init__(self, plan, x, wname, bname, Cout, k, stride, pad, transposed):
+    def __init__(self, plan, x, wname, bname, Cout, k, stride, pad, transposed, want_stats=False):
         self.plan, self.x, self.wname, self.bname = plan, x, wname, bname
         self.k, self.stride, self.pad, self.transposed, self.Cout = k, stride, pad, transposed, Cout
         self.Cin = x.C
@@ -444,11 +451,17 @@ class _Conv(_Op):
         self.want_stats = None                   # BNState set by the following bn_act (stats over this output)
         coarse = x.M if transposed else self.y.M   # algorithmic GEMM work: 2 * Cin*Cout*k*k per pixel of the coarse side
         self.flops = 2 * coarse * self.Cin * Cout * k * k
+        if plan.tc and plan.training and want_stats:
+            self.y.stats = plan.arena(2 * Cout)
         self._emit_fwd()
 
     def _emit_fwd(self):
         pl, x, y = self.plan, self.x, self.y
         b = pl.P(self.bname) if self.bname else None
+        if pl.tc:
+            pl.call(pl.fwd, "awr_conv_tc", x.t, pl.W16(self.wname), b, y.t, y.stats, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
+                    self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0, flops=self.flops, tag="conv_fprop")
+            return
         pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(self.wname), b, y.t, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
                 self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0, flops=self.flops, tag="conv_fprop")
 
@@ -458,6 +471,22 @@ class _Conv(_Op):
             return
         dy = y.grad()
         gW = pl.G(self.wname)
+        if pl.tc:
+            if not self.transposed:
+                pl.call(pl.bwd, "awr_conv_wgrad_tc", dy, x.t, gW, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k, self.stride,
+                        self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
+            else:
+                pl.call(pl.bwd, "awr_conv_wgrad_tc", x.t, dy, gW, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k, self.stride,
+                        self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
+            if self.bname:
+                pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
+            w16 = pl.W16(self.wname)
+
+            def emit_tc(dst, acc):
+                pl.call(pl.bwd, "awr_conv_tc", dy, w16, None, dst, None, y.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k, self.stride,
+                        self.pad, int(not self.transposed), self.Cin, 1, self.Cout * self.Cin, 0, 0, int(acc), flops=self.flops, tag="conv_dgrad")
+            _contribute(pl, x, emit_tc)
+            return
         # weight gradient
         if not self.transposed:
             pl.call(pl.bwd, "awr_conv_wgrad_simt", dy, x.t, gW, pl.dt, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
@@ -483,24 +512,24 @@ class _BNAct(_Op):
 
     def __init__(self, plan, y, prefix, relu, res, res_y, res_prefix):
         self.plan, self.y, self.prefix, self.relu, self.res, self.res_y, self.res_prefix = plan, y, prefix, relu, res, res_y, res_prefix
-        self.bn = BNState(plan, prefix, y.C)
-        self.bn_res = BNState(plan, res_prefix, y.C) if res_y is not None else None
+        self.bn = BNState(plan, prefix, y.C, y.stats)
+        self.bn_res = BNState(plan, res_prefix, y.C, res_y.stats) if res_y is not None else None
         self.out = Act(plan, y.N, y.H, y.W, y.C)
-        self._emit_stats(y, self.bn)
-        if res_y is not None:
-            self._emit_stats(res_y, self.bn_res)
         pl = plan
-        pl.call(pl.fwd, "awr_affine_act", y.t, self.bn.ss, (res.t if res is not None else (res_y.t if res_y is not None else None)),
-                (self.bn_res.ss if self.bn_res else None), self.out.t, pl.dt, y.M, y.C, int(relu))
+        tr = pl.training
+        for t, bn in ((y, self.bn), (res_y, self.bn_res)):
+            if bn is not None and tr and not bn.fused_stats:
+                pl.call(pl.fwd, "awr_channel_stats", t.t, pl.dt, t.M, t.C, bn.sums, 1)
 
-    def _emit_stats(self, y, bn):
-        pl = self.plan
-        p = bn.prefix
-        if pl.training:
-            pl.call(pl.fwd, "awr_channel_stats", y.t, pl.dt, y.M, y.C, bn.sums, 1)
-        pl.call(pl.fwd, "awr_bn_finalize", bn.sums if pl.training else None, y.M, pl.P(p + ".weight"), pl.P(p + ".bias"),
-                pl.buf(p + ".running_mean"), pl.buf(p + ".running_var"), pl.buf(p + ".num_batches_tracked") if pl.training else None,
-                bn.ss, bn.mi, y.C, BN_MOMENTUM, BN_EPS, int(pl.training))
+        def bnset(bn):
+            if bn is None:
+                return [None] * 7
+            p = bn.prefix
+            return [bn.sums if tr else None, pl.P(p + ".weight"), pl.P(p + ".bias"), pl.buf(p + ".running_mean"), pl.buf(p + ".running_var"),
+                    pl.buf(p + ".num_batches_tracked") if tr else None, bn.mi]
+        a, b = bnset(self.bn), bnset(self.bn_res)
+        rt = res.t if res is not None else (res_y.t if res_y is not None else None)
+        pl.call(pl.fwd, "awr_bn_act", y.t, *a, rt, *b, self.out.t, pl.dt, y.M, y.C, BN_MOMENTUM, BN_EPS, int(tr), int(relu))
 
     def plan_bwd(self):
         pl, y, out = self.plan, self.y, self.out
@@ -605,8 +634,12 @@ class _Head(_Op):
         self.dpred = torch.zeros_like(self.pred) if plan.training else None   # written by the head/loss backward (or autograd)
         self._nhwc = None
         pl = plan
-        pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(gname + ".weight"), pl.P(gname + ".bias"), self.pred, pl.dt, x.N, x.H, x.W, x.C,
-                x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
+        if pl.tc:
+            pl.call(pl.fwd, "awr_conv_tc", x.t, pl.W16(gname + ".weight"), pl.P(gname + ".bias"), self.pred, None, x.N, x.H, x.W, x.C,
+                    x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
+        else:
+            pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(gname + ".weight"), pl.P(gname + ".bias"), self.pred, pl.dt, x.N, x.H, x.W, x.C,
+                    x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
 
     def pred_nhwc(self):
         """Prediction volume as a 64-channel NHWC activation (input of merge_preds in stacked hourglasses)."""
@@ -635,6 +668,16 @@ class _Head(_Op):
             else:
                 pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, d, pl.dt, x.N, 4 * J, 64, P)
         g = self.gname
+        if pl.tc:
+            pl.call(pl.bwd, "awr_conv_wgrad_tc", d, x.t, pl.G(g + ".weight"), x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1, 64 * x.C,
+                    flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
+            pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, 64, pl.G(g + ".bias"), 0)
+
+            def emit_tc(dst, acc):
+                pl.call(pl.bwd, "awr_conv_tc", d, pl.W16(g + ".weight"), None, dst, None, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, 0,
+                        x.C, 1, 64 * x.C, 0, 0, int(acc), flops=2 * x.M * x.C * 4 * J, tag="conv_dgrad")
+            _contribute(pl, x, emit_tc)
+            return
         pl.call(pl.bwd, "awr_conv_wgrad_simt", d, x.t, pl.G(g + ".weight"), pl.dt, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1,
                 64 * x.C, flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
         pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, 64, pl.G(g + ".bias"), 0)

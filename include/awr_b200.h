@@ -71,6 +71,16 @@ int awr_bn_finalize(const float* sums, long long count, const float* gamma, cons
                     float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_invstd, int C,
                     float momentum, float eps, int training, void* stream);
 
+/* One-launch BatchNorm2d forward: out = act( BN(y) [+ res | + BN_res(res)] ).  training: batch statistics from sums[2C] = {sum, sum of
+ * squares} over the M pixels (produced by awr_channel_stats or by awr_conv_tc's epilogue), running statistics updated (momentum,
+ * unbiased variance), *num_batches_tracked += 1; eval: running statistics.  mean_invstd[2C] (or NULL) is saved for backward.
+ * The res_* set (all NULL when absent) is the BatchNorm of the residual branch (ResNet downsample path, resnet_deconv.py:62-68). */
+int awr_bn_act(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+               long long* num_batches_tracked, float* mean_invstd, const void* res, const float* res_sums, const float* res_gamma,
+               const float* res_beta, float* res_running_mean, float* res_running_var, long long* res_num_batches_tracked,
+               float* res_mean_invstd, void* out, int dtype, long long M, int C, float momentum, float eps, int training, int relu,
+               void* stream);
+
 /* out = act( ss(y) + res_ss(res) ),  ss(v)[c] = v*scale[c] + shift[c]; scale_shift / res / res_scale_shift may be NULL. */
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream);
@@ -139,10 +149,17 @@ int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int 
  * NHWC bf16 activations, bf16 weights (the Adam kernel's shadow copy, same physical order [kh][kw][Cout][Cin]), fp32
  * accumulation in TMEM, operands staged by TMA (shifted boxes = implicit im2col, zero OOB fill = padding).
  * Same argument meaning as awr_conv_simt (w strides select fprop [w_sk==1] or dgrad [w_sn==1]); Ck, Cn multiples of 64,
- * feature-map sides powers of two <= 256, stride 1 or 2.  Returns AWR_ERR_DRIVER (-3) if the driver cannot encode a tensor map. */
-int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, int N, int Hi, int Wi, int Ck, int Ho, int Wo, int Cn, int R,
-                int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode, int n_valid, int accumulate,
-                void* stream);
+ * feature-map sides powers of two <= 256, stride 1 or 2.  stats (or NULL): fp32 [2*Cn], the epilogue adds the per-channel sum and
+ * sum of squares of the (bf16-rounded) outputs -- the BatchNorm batch statistics -- so no separate reduction pass is needed
+ * (caller zero-fills).  Returns AWR_ERR_DRIVER (-3) if the driver cannot encode a tensor map. */
+int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, float* stats, int N, int Hi, int Wi, int Ck, int Ho, int Wo,
+                int Cn, int R, int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode, int n_valid,
+                int accumulate, void* stream);
+
+/* Weight gradient on tensor cores; same argument meaning as awr_conv_wgrad_simt (bf16 NHWC operands, fp32 dW accumulated with
+ * atomic adds: caller zero-fills).  The contraction runs over pixels; both operands are MN-major TMA boxes of the NHWC tensors. */
+int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
+                      int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
 
 #ifdef __cplusplus
 }

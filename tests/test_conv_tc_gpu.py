@@ -20,10 +20,18 @@ def _rb(t):
     return t.to(torch.bfloat16).float()
 
 
-def _conv_tc(x, w_phys, bias, out, N, Hi, Wi, Ck, Ho, Wo, Cn, k, stride, pad, transposed, w_sk, w_sn, w_tap, out_mode=0, n_valid=0, acc=0):
+def _conv_tc(x, w_phys, bias, out, N, Hi, Wi, Ck, Ho, Wo, Cn, k, stride, pad, transposed, w_sk, w_sn, w_tap, out_mode=0, n_valid=0, acc=0, stats=None):
     from awr_b200 import _lib as L
-    L.check(L.lib().awr_conv_tc(x.data_ptr(), w_phys.data_ptr(), None if bias is None else bias.data_ptr(), out.data_ptr(), N, Hi, Wi, Ck,
+    L.check(L.lib().awr_conv_tc(x.data_ptr(), w_phys.data_ptr(), None if bias is None else bias.data_ptr(), out.data_ptr(),
+                                None if stats is None else stats.data_ptr(), N, Hi, Wi, Ck,
                                 Ho, Wo, Cn, k, k, stride, pad, transposed, w_sk, w_sn, w_tap, out_mode, n_valid, acc, L.stream()), "awr_conv_tc")
+    torch.cuda.synchronize()
+
+
+def _wgrad_tc(pw, ga, dW, N, Hc, Wc, Cp, Hf, Wf, Cg, k, stride, pad, s_p, s_g, w_tap):
+    from awr_b200 import _lib as L
+    L.check(L.lib().awr_conv_wgrad_tc(pw.data_ptr(), ga.data_ptr(), dW.data_ptr(), N, Hc, Wc, Cp, Hf, Wf, Cg, k, k, stride, pad, s_p, s_g, w_tap,
+                                      L.stream()), "awr_conv_wgrad_tc")
     torch.cuda.synchronize()
 
 
@@ -52,14 +60,24 @@ def test_conv2d_fprop_dgrad(case):
     ref.backward(gy)
     w_phys = w.permute(2, 3, 0, 1).contiguous().to(torch.bfloat16).cuda()       # [kh][kw][Co][Ci]
     y = torch.full((N, Ho, Ho, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
-    _conv_tc(_nhwc(x), w_phys, b.cuda(), y, N, H, H, Ci, Ho, Ho, Co, k, s, pad, 0, 1, Ci, Co * Ci)
+    stats = torch.zeros(2 * Co, dtype=torch.float32, device="cuda")
+    _conv_tc(_nhwc(x), w_phys, b.cuda(), y, N, H, H, Ci, Ho, Ho, Co, k, s, pad, 0, 1, Ci, Co * Ci, stats=stats)
     got = _from_nhwc(y)
     assert (got - ref.detach()).abs().max().item() < 1e-2 * ref.abs().max().item()
+    # fused BatchNorm statistics == per-channel sum / sum of squares of the stored (bf16) output
+    s1, s2 = got.double().sum(dim=(0, 2, 3)), (got.double() ** 2).sum(dim=(0, 2, 3))
+    assert torch.allclose(stats[:Co].cpu().double(), s1, rtol=1e-4, atol=1e-2) and torch.allclose(stats[Co:].cpu().double(), s2, rtol=1e-4, atol=1e-2)
     # dgrad: dx = conv_transpose(dy, w)  -> contraction over Cout, MN-major B from the same weight buffer
     dx = torch.full((N, H, H, Ci), float("nan"), dtype=torch.bfloat16, device="cuda")
     _conv_tc(_nhwc(gy), w_phys, None, dx, N, Ho, Ho, Co, H, H, Ci, k, s, pad, 1, Ci, 1, Co * Ci)
     gdx = _from_nhwc(dx)
     assert (gdx - xr.grad).abs().max().item() < 1e-2 * xr.grad.abs().max().item()
+    # wgrad: contraction over pixels, both operands MN-major
+    ref_dw = torch.autograd.grad(F.conv2d(x.clone().requires_grad_(False), wr := w.clone().requires_grad_(True), None, stride=s, padding=pad), wr, gy)[0]
+    dW = torch.zeros(k, k, Co, Ci, dtype=torch.float32, device="cuda")
+    _wgrad_tc(_nhwc(gy), _nhwc(x), dW, N, Ho, Ho, Co, H, H, Ci, k, s, pad, Ci, 1, Co * Ci)
+    got_dw = dW.cpu().permute(2, 3, 0, 1)
+    assert (got_dw - ref_dw).abs().max().item() < 2e-3 * ref_dw.abs().max().item() + 1e-5     # fp32 accumulate of exact bf16 products
     # accumulate mode adds into the existing tensor
     _conv_tc(_nhwc(gy), w_phys, None, dx, N, Ho, Ho, Co, H, H, Ci, k, s, pad, 1, Ci, 1, Co * Ci, acc=1)
     assert (_from_nhwc(dx) - 2 * xr.grad).abs().max().item() < 2e-2 * xr.grad.abs().max().item()
@@ -81,12 +99,21 @@ def test_conv_transpose2d_fprop_dgrad(case):
     Ho = 2 * H
     w_phys = w.permute(2, 3, 1, 0).contiguous().to(torch.bfloat16).cuda()       # [kh][kw][Co][Ci]
     y = torch.full((N, Ho, Ho, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
-    _conv_tc(_nhwc(x), w_phys, None, y, N, H, H, Ci, Ho, Ho, Co, 4, 2, 1, 1, 1, Ci, Co * Ci)
+    stats = torch.zeros(2 * Co, dtype=torch.float32, device="cuda")
+    _conv_tc(_nhwc(x), w_phys, None, y, N, H, H, Ci, Ho, Ho, Co, 4, 2, 1, 1, 1, Ci, Co * Ci, stats=stats)
     got = _from_nhwc(y)
     assert (got - ref.detach()).abs().max().item() < 1e-2 * ref.abs().max().item()
+    s1, s2 = got.double().sum(dim=(0, 2, 3)), (got.double() ** 2).sum(dim=(0, 2, 3))
+    assert torch.allclose(stats[:Co].cpu().double(), s1, rtol=1e-4, atol=1e-2) and torch.allclose(stats[Co:].cpu().double(), s2, rtol=1e-4, atol=1e-2)
     dx = torch.full((N, H, H, Ci), float("nan"), dtype=torch.bfloat16, device="cuda")
     _conv_tc(_nhwc(gy), w_phys, None, dx, N, Ho, Ho, Co, H, H, Ci, 4, 2, 1, 0, Ci, 1, Co * Ci)
     assert (_from_nhwc(dx) - xr.grad).abs().max().item() < 1e-2 * xr.grad.abs().max().item()
+    wr = w.clone().requires_grad_(True)
+    ref_dw = torch.autograd.grad(F.conv_transpose2d(x, wr, None, stride=2, padding=1), wr, gy)[0]      # (Ci,Co,4,4)
+    dW = torch.zeros(4, 4, Co, Ci, dtype=torch.float32, device="cuda")
+    _wgrad_tc(_nhwc(x), _nhwc(gy), dW, N, H, H, Ci, Ho, Ho, Co, 4, 2, 1, 1, Ci, Co * Ci)
+    got_dw = dW.cpu().permute(3, 2, 0, 1)
+    assert (got_dw - ref_dw).abs().max().item() < 2e-3 * ref_dw.abs().max().item() + 1e-5
 
 
 def test_head_conv_nchw_fp32_output():

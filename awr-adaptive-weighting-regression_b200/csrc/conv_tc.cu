@@ -57,6 +57,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int b_bytes = p.Ntile * 128;
   const int stage_bytes = kABytes + b_bytes;
   const int total_tiles = p.nclasses * p.tiles_m * p.tiles_c;
+  // per-CTA BatchNorm partial sums [2*Cn] (fp32) behind the pipeline stages: flushed with one global atomic per channel at the end
+  float* s_stats = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes);
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * p.Cn; i += kThreads) s_stats[i] = 0.f;
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -160,8 +165,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
         if (bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + c0 + ch);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] += __ldg(bias + c0 + ch + i);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(b4 + i);
+            f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+          }
         }
         if (stats) {
           // per-channel sum / sum of squares of the bf16-rounded outputs (what BatchNorm will normalise): 32x32 transpose-
@@ -183,8 +192,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               s2[i] = k2 + __shfl_xor_sync(0xffffffffu, d2, st);
             }
           }
-          atomicAdd(stats + c0 + ch + lane, s1[0]);
-          atomicAdd(stats + p.Cn + c0 + ch + lane, s2[0]);
+          atomicAdd(s_stats + c0 + ch + lane, s1[0]);
+          atomicAdd(s_stats + p.Cn + c0 + ch + lane, s2[0]);
           if (!valid) continue;
         }
         if (p.out_mode == 0) {
@@ -220,6 +229,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (stats) {
+    for (int i = threadIdx.x; i < 2 * p.Cn; i += kThreads) {
+      const float v = s_stats[i];
+      if (v != 0.f) atomicAdd(stats + i, v);
+    }
+  }
   if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -286,9 +301,10 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
   }
   p.tiles_c = Cn / p.Ntile;
   const int stage_bytes = kABytes + p.Ntile * 128;
-  p.stages = (200 * 1024) / stage_bytes;
+  const int stats_bytes = stats ? 2 * Cn * (int)sizeof(float) : 0;
+  p.stages = (200 * 1024 - stats_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + stats_bytes;
 
   CUtensorMap tmA, tmB;
   {

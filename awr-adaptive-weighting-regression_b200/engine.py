@@ -257,7 +257,7 @@ class Plan:
             raise RuntimeError("plan arena exhausted")
         return self.arena_buf[off: off + n]
 
-    def call(self, lst, fn, *args, flops=0, nbytes=0, tag=None):
+    def call(self, lst, fn, *args, flops=0, nbytes=0, tag=None, detail=""):
         """Bind a C-ABI launch. Tensor-like args are resolved to pointers now (buffers are static).
         flops / nbytes: algorithmic work of this launch (for the roofline report); tag: kernel class label."""
         cargs = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
@@ -269,7 +269,7 @@ class Plan:
             if rc != 0:
                 L.check(rc, name)
         lst.append(run)
-        (self.fwd_meta if lst is self.fwd else self.bwd_meta).append((tag or fn, flops, nbytes))
+        (self.fwd_meta if lst is self.fwd else self.bwd_meta).append((tag or fn, flops, nbytes, detail))
 
     def P(self, name):
         return self.store.layout.phys(self.store.params, name)
@@ -451,6 +451,7 @@ class _Conv(_Op):
         self.want_stats = None                   # BNState set by the following bn_act (stats over this output)
         coarse = x.M if transposed else self.y.M   # algorithmic GEMM work: 2 * Cin*Cout*k*k per pixel of the coarse side
         self.flops = 2 * coarse * self.Cin * Cout * k * k
+        self.detail = f"{'deconv' if transposed else 'conv'}{k}x{k}s{stride} {self.Cin}->{Cout} @{x.H}->{Ho} N{x.N}"
         if plan.tc and plan.training and want_stats:
             self.y.stats = plan.arena(2 * Cout)
         self._emit_fwd()
@@ -460,10 +461,10 @@ class _Conv(_Op):
         b = pl.P(self.bname) if self.bname else None
         if pl.tc:
             pl.call(pl.fwd, "awr_conv_tc", x.t, pl.W16(self.wname), b, y.t, y.stats, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
-                    self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0, flops=self.flops, tag="conv_fprop")
+                    self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0, flops=self.flops, tag="conv_fprop", detail=self.detail)
             return
         pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(self.wname), b, y.t, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
-                self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0, flops=self.flops, tag="conv_fprop")
+                self.stride, self.pad, int(self.transposed), 1, self.Cin, self.Cout * self.Cin, 0, 0, 0, flops=self.flops, tag="conv_fprop", detail=self.detail)
 
     def plan_bwd(self):
         pl, x, y = self.plan, self.x, self.y
@@ -474,26 +475,26 @@ class _Conv(_Op):
         if pl.tc:
             if not self.transposed:
                 pl.call(pl.bwd, "awr_conv_wgrad_tc", dy, x.t, gW, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k, self.stride,
-                        self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
+                        self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
             else:
                 pl.call(pl.bwd, "awr_conv_wgrad_tc", x.t, dy, gW, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k, self.stride,
-                        self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
+                        self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
             if self.bname:
                 pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
             w16 = pl.W16(self.wname)
 
             def emit_tc(dst, acc):
                 pl.call(pl.bwd, "awr_conv_tc", dy, w16, None, dst, None, y.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k, self.stride,
-                        self.pad, int(not self.transposed), self.Cin, 1, self.Cout * self.Cin, 0, 0, int(acc), flops=self.flops, tag="conv_dgrad")
+                        self.pad, int(not self.transposed), self.Cin, 1, self.Cout * self.Cin, 0, 0, int(acc), flops=self.flops, tag="conv_dgrad", detail=self.detail)
             _contribute(pl, x, emit_tc)
             return
         # weight gradient
         if not self.transposed:
             pl.call(pl.bwd, "awr_conv_wgrad_simt", dy, x.t, gW, pl.dt, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
-                    self.stride, self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
+                    self.stride, self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
         else:
             pl.call(pl.bwd, "awr_conv_wgrad_simt", x.t, dy, gW, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
-                    self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad")
+                    self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
         if self.bname:
             pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
         # data gradient
@@ -503,7 +504,7 @@ class _Conv(_Op):
             def emit(dst, acc):
                 pl.call(pl.bwd, "awr_conv_simt", dy, w, None, dst, pl.dt, y.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
                         self.stride, self.pad, int(not self.transposed), self.Cin, 1, self.Cout * self.Cin, 0, 0, int(acc),
-                        flops=self.flops, tag="conv_dgrad")
+                        flops=self.flops, tag="conv_dgrad", detail=self.detail)
             _contribute(pl, x, emit)
 
 

@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg (0 disables)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--layers", default="", help="write a per-layer conv timing table to gpurun_out/<name>")
     return ap.parse_args()
 
 
@@ -146,7 +147,7 @@ class Clocks:
 # ---------------------------------------------------------------------------------------------------------
 # per-kernel-class device timing of one eager step (CUDA events on the launch stream, queue pre-filled behind a spin)
 # ---------------------------------------------------------------------------------------------------------
-def classify_step(tr, steps):
+def classify_step(tr, steps, layers=None):
     import torch
     from awr_b200 import _lib as L
     pl = tr.plan
@@ -176,9 +177,14 @@ def classify_step(tr, steps):
             evs.append((m, e0, e1))
         tr._opt()
         torch.cuda.synchronize()
-        for (tag, fl, nb), e0, e1 in evs:
+        for m, e0, e1 in evs:
+            tag, fl, nb = m[0], m[1], m[2]
             a = agg.setdefault(tag, [0.0, 0, 0, 0])
-            a[0] += e0.elapsed_time(e1); a[1] += fl; a[2] += nb; a[3] += 1
+            dt = e0.elapsed_time(e1)
+            a[0] += dt; a[1] += fl; a[2] += nb; a[3] += 1
+            if layers is not None and len(m) > 3 and m[3]:
+                l = layers.setdefault((tag, m[3]), [0.0, fl, 0])
+                l[0] += dt; l[2] += 1
     return agg
 
 
@@ -280,7 +286,15 @@ def main():
     classes = {}
     if rank == 0:
         pk = peaks()
-        agg = classify_step(tr, 3)
+        layers = {} if a.layers else None
+        agg = classify_step(tr, 3, layers)
+        if layers:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", a.layers), "w") as f:
+                f.write("| kernel | layer | launches/step | us/launch | TFLOP/s |\n|---|---|---:|---:|---:|\n")
+                for (tag, det), (ms_, fl, n_) in sorted(layers.items(), key=lambda kv: -kv[1][0]):
+                    us = 1e3 * ms_ / n_
+                    f.write(f"| {tag} | {det} | {n_ // 3} | {us:.1f} | {fl / (us * 1e-6) / 1e12:.1f} |\n")
         tot = sum(v[0] for v in agg.values())
         classes = {k: {"ms_per_step": round(v[0] / 3, 4), "share": round(v[0] / tot, 4), "launches_per_step": v[3] // 3} for k, v in
                    sorted(agg.items(), key=lambda kv: -kv[1][0])}

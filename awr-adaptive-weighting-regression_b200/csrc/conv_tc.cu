@@ -45,6 +45,17 @@ struct ConvTcParams {
   TapClass cls[kMaxClasses];
 };
 
+#ifdef AWR_CONV_PROFILE
+// debug-only role timers (cycles, summed per CTA): [0] producer wait-empty, [1] mma wait-full, [2] mma wait-tmem-empty, [3] epilogue
+// wait-tmem-full, [4] epilogue busy, [5] kernel total, [6] tiles, [7] k-iterations
+__device__ unsigned long long g_conv_prof[148 * 8];
+#define PROF_T0() const long long t0__ = clock64()
+#define PROF_ADD(slot) atomicAdd(&g_conv_prof[blockIdx.x * 8 + (slot)], (unsigned long long)(clock64() - t0__))
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
                void* __restrict__ outp, float* __restrict__ stats, const __grid_constant__ ConvTcParams p) {
@@ -53,6 +64,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef AWR_CONV_PROFILE
+  const long long k_t0 = clock64();
+#endif
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_bytes = p.Ntile * 128;
   const int stage_bytes = kABytes + b_bytes;
@@ -90,7 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int t = 0; t < tc_.ntaps; ++t) {
           const int ax = w0 * p.a_stride + tc_.ox[t], ay = h0 * p.a_stride + tc_.oy[t], wi = tc_.widx[t];
           for (int kc = 0; kc < p.kblocks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            { PROF_T0(); mbar_wait(&empty_bar[stage], phase ^ 1u); PROF_ADD(0); }
             mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
             uint8_t* sa = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes;
             tma_load_4d(sa, &tmA, &full_bar[stage], kc * 64, ax, ay, n0);
@@ -107,33 +121,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =======================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.Ntile, 0, p.b_mn);
-      int stage = 0; uint32_t phase = 0;
-      int as = 0; uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int c = (tile / p.tiles_c) / p.tiles_m;
-        const int iters = p.cls[c].ntaps * p.kblocks;
-        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+    // whole warp walks the barriers; one elected lane issues.  Descriptors are built once: per k-iteration only the 14-bit
+    // start-address field moves (stage offset, +32 B per UMMA_K for K-major / +2048 B for MN-major operands).
+    const uint32_t idesc = umma_idesc_bf16(128, p.Ntile, 0, p.b_mn);
+    const uint64_t adesc0 = umma_desc_sw128(smem_base, 16, 1024);
+    const uint64_t bdesc0 = p.b_mn ? umma_desc_sw128(smem_base + kABytes, 8192, 1024) : umma_desc_sw128(smem_base + kABytes, 16, 1024);
+    const uint32_t bstep = p.b_mn ? (2048u >> 4) : (32u >> 4);
+    const uint32_t sstep = (uint32_t)stage_bytes >> 4;
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int c = (tile / p.tiles_c) / p.tiles_m;
+      const int iters = p.cls[c].ntaps * p.kblocks;
+      { PROF_T0(); mbar_wait(&tempty_bar[as], aphase ^ 1u); if (lane == 0) PROF_ADD(2); }
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.Ntile);
+      for (int it = 0; it < iters; ++it) {
+        { PROF_T0(); mbar_wait(&full_bar[stage], phase); if (lane == 0) PROF_ADD(1); }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.Ntile);
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)(stage * stage_bytes), sb = sa + kABytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bd = p.b_mn ? umma_desc_sw128(sb + k * 2048, 8192, 1024) : umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (it | k) ? 1u : 0u);
-          }
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * sstep);
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)stage * sstep);
+          umma_bf16(d_tmem, ad, bd, idesc, it ? 1u : 0u);
+          umma_bf16(d_tmem, ad + 2, bd + bstep, idesc, 1u);
+          umma_bf16(d_tmem, ad + 4, bd + 2 * bstep, idesc, 1u);
+          umma_bf16(d_tmem, ad + 6, bd + 3 * bstep, idesc, 1u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (elect_one()) {
         if (iters > 0) umma_commit(&tfull_bar[as]);
         else mbar_arrive(&tfull_bar[as]);
-        if (++as == 2) { as = 0; aphase ^= 1u; }
       }
+      __syncwarp();
+      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else {
     // ======================================= epilogue =======================================
@@ -150,7 +173,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = n < p.N && hc < p.Hc && wc < p.Wc;
       const int ho = hc * p.out_s + p.cls[c].py, wo = wc * p.out_s + p.cls[c].px;
       const bool has_acc = p.cls[c].ntaps > 0;
-      mbar_wait(&tfull_bar[as], aphase);
+      if (warp == 2 && lane == 0) { PROF_T0(); mbar_wait(&tfull_bar[as], aphase); PROF_ADD(3); }
+      else mbar_wait(&tfull_bar[as], aphase);
+#ifdef AWR_CONV_PROFILE
+      const long long e_t0 = clock64();
+#endif
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.Ntile);
       for (int ch = 0; ch < p.Ntile; ch += 32) {
@@ -223,6 +250,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
+#ifdef AWR_CONV_PROFILE
+      if (warp == 2 && lane == 0) {
+        atomicAdd(&g_conv_prof[blockIdx.x * 8 + 4], (unsigned long long)(clock64() - e_t0));
+        atomicAdd(&g_conv_prof[blockIdx.x * 8 + 6], 1ull);
+        atomicAdd(&g_conv_prof[blockIdx.x * 8 + 7], (unsigned long long)(p.cls[c].ntaps * p.kblocks));
+      }
+#endif
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
@@ -236,9 +270,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+#ifdef AWR_CONV_PROFILE
+  if (threadIdx.x == 0) atomicAdd(&g_conv_prof[blockIdx.x * 8 + 5], (unsigned long long)(clock64() - k_t0));
+#endif
 }
 
 }  // namespace
+
+#ifdef AWR_CONV_PROFILE
+extern "C" int awr_debug_conv_profile(unsigned long long* out_host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out_host, g_conv_prof, sizeof(g_conv_prof));
+  if (reset) { static unsigned long long z[148 * 8]; cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 extern "C" {
 

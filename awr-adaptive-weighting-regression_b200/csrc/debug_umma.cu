@@ -1,0 +1,84 @@
+// Hardware probe (debug): can a SWIZZLE_128B K-major UMMA operand be a ROW-SHIFTED window of a larger TMA-written smem tile?
+//
+// G (rows x 64 bf16) is loaded by one TMA box into smem (SWIZZLE_128B).  A = the 128 rows selected by the descriptor
+//   row(m) = r0 + (m / 8) * (sbo_rows) + (m % 8),   start address = tile + r0 * 128 B, SBO = sbo_rows * 128 B,
+// B = Bm (64 x 64, K-major).  D[128 x 64] = A * Bm^T is written as fp32.  base_mode: 0 -> descriptor base_offset 0,
+// 1 -> base_offset = (start_address >> 7) & 7 (PTX matrix-descriptor rule for non-1024-B-aligned starts).
+// This decides whether conv taps can be fed from ONE halo tile (design note in DESIGN.md, "operand reuse").
+#include "tc_common.cuh"
+#include "awr_b200.h"
+
+namespace {
+using namespace tc;
+
+__global__ void __launch_bounds__(128, 1)
+umma_window_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmB, float* __restrict__ D, int rows, int r0,
+                   int sbo_rows, int base_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar, done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sb = sg + rows * 128;
+  if (threadIdx.x == 0) { mbar_init(&full_bar, 1); mbar_init(&done_bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&full_bar, (uint32_t)(rows * 128 + 64 * 128));
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(sg)),
+                 "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(smem_u32(&full_bar)), "r"(0), "r"(0)
+                 : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(sb)),
+                 "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&full_bar)), "r"(0), "r"(0)
+                 : "memory");
+    mbar_wait(&full_bar, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    const uint32_t a_addr = base + (uint32_t)r0 * 128u;
+    uint64_t ad = umma_desc_sw128(a_addr, 16, (uint32_t)sbo_rows * 128u);
+    if (base_mode == 1) ad |= (uint64_t)((a_addr >> 7) & 7u) << 49;
+    const uint64_t bd = umma_desc_sw128(base + (uint32_t)rows * 128u, 16, 1024);
+    for (int k = 0; k < 4; ++k) umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, k ? 1u : 0u);
+    umma_commit(&done_bar);
+  }
+  __syncthreads();
+  mbar_wait(&done_bar, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int ch = 0; ch < 64; ch += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ch, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) D[row * 64 + ch + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 64); }
+}
+}  // namespace
+
+extern "C" int awr_debug_umma_window(const void* G, const void* Bm, float* D, int rows, int r0, int sbo_rows, int base_mode, void* stream) {
+  AWR_HOST_CHECK(G && Bm && D && rows >= 128 && rows <= 256 && r0 >= 0 && sbo_rows >= 8);
+  AWR_HOST_CHECK(r0 + 15 * sbo_rows + 8 <= rows);
+  CUtensorMap tmG, tmB;
+  {
+    const long long dims[2] = {64, rows}, str[2] = {1, 64};
+    const int box[2] = {64, rows};
+    if (!make_tmap_bf16(&tmG, G, 2, dims, str, box, nullptr)) return AWR_ERR_DRIVER;
+  }
+  {
+    const long long dims[2] = {64, 64}, str[2] = {1, 64};
+    const int box[2] = {64, 64};
+    if (!make_tmap_bf16(&tmB, Bm, 2, dims, str, box, nullptr)) return AWR_ERR_DRIVER;
+  }
+  const size_t smem = (size_t)rows * 128 + 64 * 128 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(umma_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  umma_window_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmG, tmB, D, rows, r0, sbo_rows, base_mode);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}

@@ -50,6 +50,20 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
                : "memory");
 }
 
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom: lets ptxas keep the tcgen05/TMA operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 r;\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync r|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");

@@ -161,6 +161,11 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
 int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
                       int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
 
+/* ---- debug / hardware probes (not on the product path) -------------------------------------------------------------- */
+/* D[128][64] fp32 = A * Bm^T where A is the row-shifted window {r0 + (m/8)*sbo_rows + m%8} of the TMA-loaded smem tile G[rows][64]
+ * (bf16, SWIZZLE_128B); probes UMMA descriptor start-address / SBO / base-offset semantics (tools/dbg_umma_window.py). */
+int awr_debug_umma_window(const void* G, const void* Bm, float* D, int rows, int r0, int sbo_rows, int base_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,51 @@
+"""Data-parallel plumbing: one process per GPU, batch sharding, ONE all-reduce of the flat gradient buffer per step.
+
+The reference is single-GPU (train.py:29,233); the path shards naturally on batch (SURVEY.md section 8 e): every frame is
+independent except train-mode BN statistics (kept per replica, like the reference's batch-32 behaviour) and the `mean`
+of the two losses (equal shards => averaged gradients == gradient of the global mean).  The collective is a plain
+NCCL sum over NVLink (gloo in CPU tests); the 1/world factor is folded into the fused Adam kernel (grad_scale).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None, device=None):
+    """torchrun-style rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*).  Returns (rank, local_rank, world)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, **kw)
+    return rank, local, world
+
+
+def shard_slice(rank, per_rank_batch):
+    """Frames [rank*B, (rank+1)*B) of the global batch belong to `rank`."""
+    return slice(rank * per_rank_batch, (rank + 1) * per_rank_batch)
+
+
+def allreduce_sum_(flat, group=None):
+    """In-place sum of the flat gradient buffer over all replicas (no-op for a single process)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+def broadcast_(tensors, src=0, group=None):
+    """DDP-style start: every replica takes `src`'s parameters / buffers."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+
+
+def max_over_ranks(value, device):
+    """Timing rule: a multi-GPU duration is the MAX over ranks."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([float(value)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+    return float(value)

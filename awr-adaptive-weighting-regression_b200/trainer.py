@@ -15,6 +15,7 @@ Semantics kept from train.py: loss = coord_weight*SmoothL1(uvd, jt) + dense_weig
 import torch
 
 from . import _lib as L
+from . import dp
 from .modules import AWRBackbone
 
 
@@ -81,8 +82,7 @@ class FusedTrainer:
 
     def _allreduce(self):
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.store.grads, op=dist.ReduceOp.SUM, group=self.pg)
+            dp.allreduce_sum_(self.store.grads, self.pg)        # NCCL over NVLink; 1/world is applied inside awr_adam_flat
 
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
@@ -131,10 +131,7 @@ class FusedTrainer:
     def broadcast_parameters(self, src=0):
         """DDP-style start: every replica takes rank `src`'s parameters and BN buffers."""
         if self.world > 1:
-            import torch.distributed as dist
-            dist.broadcast(self.store.params, src=src, group=self.pg)
-            for b in self.store.buffers.values():
-                dist.broadcast(b, src=src, group=self.pg)
+            dp.broadcast_([self.store.params] + list(self.store.buffers.values()), src, self.pg)
             if self.plan.precision == "bf16":
                 self.store.refresh_shadow()
 

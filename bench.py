@@ -197,17 +197,14 @@ def main():
     import awr_b200
     from awr_b200.trainer import FusedTrainer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from awr_b200 import dp
+    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (sm_100a kernels; there is no CPU fallback)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local, world = dp.init_from_env("nccl", dev)
     ds, ks = 2, (1.0 if a.net.startswith("resnet") else 0.4)
 
     torch.manual_seed(1)
@@ -256,9 +253,7 @@ def main():
     barrier()
     t1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
-    losses = tr.loss.tolist()
+    ms = dp.max_over_ranks(ms, dev)
     value = a.batch * world * a.steps / (ms * 1e-3)
 
     # ---- end-to-end leg: host pinned batch -> train_step -> host losses ----------------------------------
@@ -272,8 +267,7 @@ def main():
     barrier()
     t2 = time.perf_counter()
     ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = t.item()
+    ms_e2e = dp.max_over_ranks(ms_e2e, dev)
     e2e = a.batch * world * a.steps / (ms_e2e * 1e-3)
     h2d = host_batches[0][0].numel() * 4 + host_batches[0][1].numel() * 4
     clocks = None

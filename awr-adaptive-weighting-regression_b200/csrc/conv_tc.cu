@@ -9,13 +9,14 @@
 // ConvTranspose2d fprop / stride-2 Conv2d dgrad are decomposed into stride^2 output-parity classes, each a dense
 // small-tap convolution whose epilogue stores to the strided output positions (no zero insertion).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 =
+// Warp roles (192 threads): warp 4 = TMA producer, warp 5 = TMEM allocator + MMA issuer (one elected lane), warps 0..3 =
 // epilogue (TMEM -> registers -> bias/accumulate -> global).  smem ring of kStages {A,B} tiles with full/empty mbarriers,
 // two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, static tile schedule.
 //
 // Replaces nn.Conv2d / nn.ConvTranspose2d (+autograd) of model/resnet_deconv.py:31-53,78-86,141-142,182-188 and
 // model/hourglass.py:10 in the bf16 precision mode.
 #include "tc_common.cuh"
+#include "conv_tc_shared.h"
 #include "awr_b200.h"
 
 namespace {
@@ -23,14 +24,11 @@ namespace {
 using namespace tc;
 
 constexpr int kThreads = 192;
-constexpr int kMaxTaps = 16;
-constexpr int kMaxClasses = 4;
+constexpr int kMaxTaps = kConvMaxTaps;
+constexpr int kMaxClasses = kConvMaxClasses;
 constexpr int kABytes = 128 * 128;          // 128 pixels x 64 bf16
 
-struct TapClass {
-  int ntaps, py, px, pad_;
-  short oy[kMaxTaps], ox[kMaxTaps], widx[kMaxTaps];
-};
+typedef ConvTapClass TapClass;
 
 struct ConvTcParams {
   int N, Hc, Wc;                 // coarse (tile) grid
@@ -84,13 +82,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  if (warp == 5) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
+  if (warp == 4) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -119,7 +117,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // ======================================= MMA issuer =======================================
     // whole warp walks the barriers; one elected lane issues.  Descriptors are built once: per k-iteration only the 14-bit
     // start-address field moves (stage offset, +32 B per UMMA_K for K-major / +2048 B for MN-major operands).
@@ -173,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = n < p.N && hc < p.Hc && wc < p.Wc;
       const int ho = hc * p.out_s + p.cls[c].py, wo = wc * p.out_s + p.cls[c].px;
       const bool has_acc = p.cls[c].ntaps > 0;
-      if (warp == 2 && lane == 0) { PROF_T0(); mbar_wait(&tfull_bar[as], aphase); PROF_ADD(3); }
+      if (warp == 0 && lane == 0) { PROF_T0(); mbar_wait(&tfull_bar[as], aphase); PROF_ADD(3); }
       else mbar_wait(&tfull_bar[as], aphase);
 #ifdef AWR_CONV_PROFILE
       const long long e_t0 = clock64();
@@ -251,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
 #ifdef AWR_CONV_PROFILE
-      if (warp == 2 && lane == 0) {
+      if (warp == 0 && lane == 0) {
         atomicAdd(&g_conv_prof[blockIdx.x * 8 + 4], (unsigned long long)(clock64() - e_t0));
         atomicAdd(&g_conv_prof[blockIdx.x * 8 + 6], 1ull);
         atomicAdd(&g_conv_prof[blockIdx.x * 8 + 7], (unsigned long long)(p.cls[c].ntaps * p.kblocks));
@@ -269,7 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (v != 0.f) atomicAdd(stats + i, v);
     }
   }
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 5) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 #ifdef AWR_CONV_PROFILE
   if (threadIdx.x == 0) atomicAdd(&g_conv_prof[blockIdx.x * 8 + 5], (unsigned long long)(clock64() - k_t0));
 #endif
@@ -286,6 +284,21 @@ extern "C" int awr_debug_conv_profile(unsigned long long* out_host, int reset) {
 }
 #endif
 
+// bf16 weight matrix [tap][Cout][Cin] as a 3-D tensor map: K-major boxes (64 k, Ntile n) for fprop, MN-major boxes (64 n, 64 k) for dgrad
+bool conv_make_weight_map(CUtensorMap* m, const ConvGeom& g, const void* w, int Ntile) {
+  const int T = g.R * g.S;
+  if (!g.b_mn) {
+    const long long dims[3] = {g.Ck, g.Cn, T};
+    const long long str[3] = {1, g.w_sn, T > 1 ? g.w_tap : (long long)g.Cn * g.w_sn};
+    const int box[3] = {64, Ntile, 1};
+    return tc::make_tmap_bf16(m, w, 3, dims, str, box, nullptr);
+  }
+  const long long dims[3] = {g.Cn, g.Ck, T};
+  const long long str[3] = {1, g.w_sk, T > 1 ? g.w_tap : (long long)g.Ck * g.w_sk};
+  const int box[3] = {64, 64, 1};
+  return tc::make_tmap_bf16(m, w, 3, dims, str, box, nullptr);
+}
+
 extern "C" {
 
 int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, float* stats, int N, int Hi, int Wi, int Ck, int Ho, int Wo,
@@ -297,36 +310,27 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
   AWR_HOST_CHECK(w_tap % 8 == 0 || R * S == 1);
   AWR_HOST_CHECK(out_mode == 0 || (out_mode == 1 && n_valid > 0 && n_valid <= Cn && !accumulate));
   AWR_HOST_CHECK(stats == nullptr || (out_mode == 0 && !accumulate));
-  ConvTcParams p;
-  memset(&p, 0, sizeof(p));
-  // coarse grid = the tensor whose pixels index GEMM rows
+  // geometry shared by both kernels
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
   const int cs = (transposed && stride > 1) ? stride : 1;     // output pixels per coarse pixel (parity classes)
   AWR_HOST_CHECK(Ho % cs == 0 && Wo % cs == 0);
-  p.N = N; p.Hc = Ho / cs; p.Wc = Wo / cs;
-  AWR_HOST_CHECK(is_pow2(p.Wc) && is_pow2(p.Hc) && p.Wc <= 256 && p.Hc <= 256);
-  p.Wt = p.Wc < 128 ? p.Wc : 128;
-  p.Ht = (128 / p.Wt) < p.Hc ? (128 / p.Wt) : p.Hc;
-  p.Nt = 128 / (p.Wt * p.Ht);
-  p.lgWt = ilog2(p.Wt); p.lgHt = ilog2(p.Ht);
-  p.tiles_w = p.Wc / p.Wt; p.tiles_h = p.Hc / p.Ht; p.tiles_n_img = (N + p.Nt - 1) / p.Nt;
-  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n_img;
-  p.kblocks = Ck / 64;
-  p.a_stride = (!transposed) ? stride : 1;
-  AWR_HOST_CHECK(p.Wt * p.a_stride <= 256 && p.Ht * p.a_stride <= 256);
-  p.b_mn = (w_sn == 1 && w_sk != 1) ? 1 : 0;
-  p.Ho = Ho; p.Wo = Wo; p.Cn = Cn; p.out_s = cs;
-  p.out_mode = out_mode; p.n_valid = n_valid; p.accumulate = accumulate;
-  // tap classes
+  g.N = N; g.Hi = Hi; g.Wi = Wi; g.Ck = Ck; g.Ho = Ho; g.Wo = Wo; g.Cn = Cn;
+  g.Hc = Ho / cs; g.Wc = Wo / cs; g.out_s = cs;
+  g.a_stride = (!transposed) ? stride : 1;
+  g.R = R; g.S = S; g.w_sk = w_sk; g.w_sn = w_sn; g.w_tap = w_tap; g.b_mn = (w_sn == 1 && w_sk != 1) ? 1 : 0;
+  g.out_mode = out_mode; g.n_valid = n_valid; g.accumulate = accumulate;
+  AWR_HOST_CHECK(is_pow2(g.Wc) && is_pow2(g.Hc) && g.Wc <= 256 && g.Hc <= 256);
   if (!transposed) {            // in = out*stride - pad + tap
-    p.nclasses = 1;
-    TapClass& c = p.cls[0];
+    g.nclasses = 1;
+    TapClass& c = g.cls[0];
     for (int r = 0; r < R; ++r)
       for (int s = 0; s < S; ++s) { c.oy[c.ntaps] = (short)(r - pad); c.ox[c.ntaps] = (short)(s - pad); c.widx[c.ntaps] = (short)(r * S + s); ++c.ntaps; }
   } else {                      // in = (out + pad - tap) / stride, only where divisible
-    p.nclasses = cs * cs;
+    g.nclasses = cs * cs;
     for (int py = 0; py < cs; ++py)
       for (int px = 0; px < cs; ++px) {
-        TapClass& c = p.cls[py * cs + px];
+        TapClass& c = g.cls[py * cs + px];
         c.py = py; c.px = px;
         for (int r = 0; r < R; ++r) {
           if ((py + pad - r) % cs != 0) continue;
@@ -338,6 +342,25 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
         }
       }
   }
+  if (conv_halo_supported(g) && !getenv("AWR_B200_NO_HALO")) return conv_halo_launch(g, in, w, bias, out, stats, (cudaStream_t)stream);
+
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.Hc = g.Hc; p.Wc = g.Wc;
+  p.Wt = p.Wc < 128 ? p.Wc : 128;
+  p.Ht = (128 / p.Wt) < p.Hc ? (128 / p.Wt) : p.Hc;
+  p.Nt = 128 / (p.Wt * p.Ht);
+  p.lgWt = ilog2(p.Wt); p.lgHt = ilog2(p.Ht);
+  p.tiles_w = p.Wc / p.Wt; p.tiles_h = p.Hc / p.Ht; p.tiles_n_img = (N + p.Nt - 1) / p.Nt;
+  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n_img;
+  p.kblocks = Ck / 64;
+  p.a_stride = g.a_stride;
+  AWR_HOST_CHECK(p.Wt * p.a_stride <= 256 && p.Ht * p.a_stride <= 256);
+  p.b_mn = g.b_mn;
+  p.Ho = Ho; p.Wo = Wo; p.Cn = Cn; p.out_s = cs;
+  p.out_mode = out_mode; p.n_valid = n_valid; p.accumulate = accumulate;
+  p.nclasses = g.nclasses;
+  for (int c = 0; c < g.nclasses; ++c) p.cls[c] = g.cls[c];
   // N tile: the largest of {256,128,64} dividing Cn that still yields >= 148 tiles, else the smallest
   const int cand[3] = {256, 128, 64};
   p.Ntile = 64;
@@ -360,20 +383,7 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
     const int es[4] = {1, p.a_stride, p.a_stride, 1};
     if (!make_tmap_bf16(&tmA, in, 4, dims, str, box, es)) return AWR_ERR_DRIVER;
   }
-  {
-    const int T = R * S;
-    if (!p.b_mn) {
-      const long long dims[3] = {Ck, Cn, T};
-      const long long str[3] = {1, w_sn, T > 1 ? w_tap : (long long)Cn * w_sn};
-      const int box[3] = {64, p.Ntile, 1};
-      if (!make_tmap_bf16(&tmB, w, 3, dims, str, box, nullptr)) return AWR_ERR_DRIVER;
-    } else {
-      const long long dims[3] = {Cn, Ck, T};
-      const long long str[3] = {1, w_sk, T > 1 ? w_tap : (long long)Ck * w_sk};
-      const int box[3] = {64, 64, 1};
-      if (!make_tmap_bf16(&tmB, w, 3, dims, str, box, nullptr)) return AWR_ERR_DRIVER;
-    }
-  }
+  if (!conv_make_weight_map(&tmB, g, w, p.Ntile)) return AWR_ERR_DRIVER;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);

@@ -59,7 +59,142 @@ umma_window_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constan
   __syncthreads();
   if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 64); }
 }
+
+// MMA-rate probe: one CTA per SM issues `iters` x 4 back-to-back tcgen05.mma (M=128, N, K=16) from fixed smem operands, cycling over
+// `nacc` independent accumulators; no TMA traffic, no epilogue.  out[blockIdx] = cycles from first issue to completion of the last.
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* out, int N, int nacc, int iters, int a_rows_shift) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t* z = reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)));
+  for (int i = threadIdx.x; i < (48 * 1024) / 4; i += 128) z[i] = 0x3c003c00u + i;
+  if (threadIdx.x == 0) { mbar_init(&done_bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+    const uint64_t ad = umma_desc_sw128(base + a_rows_shift * 128, 16, 1024), bd = umma_desc_sw128(base + 16384, 16, 1024);
+    long long t0 = 0;
+    if (elect_one()) {
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t d = tmem + (uint32_t)((it % nacc) * N);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, 1u);
+      }
+      umma_commit(&done_bar);
+    }
+    __syncwarp();
+    mbar_wait(&done_bar, 0);
+    if (elect_one()) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 512); }
+}
+
+
+// Pipeline probe: the MMA-issuer loop of the conv kernels without epilogue.  mode bit0: tcgen05.commit to an mbarrier per group of
+// `per` MMAs; bit1: mbarrier wait (on a barrier completed by that commit chain = "empty->full" ping) per group; bit2: a producer
+// warp refills a `stages`-deep ring with 2-D TMA boxes of `tma_rows` x 128 B per group and the issuer waits for them (full pipeline).
+__global__ void __launch_bounds__(128, 1)
+umma_pipe_kernel(const __grid_constant__ CUtensorMap tmG, unsigned long long* out, int N, int per, int groups, int mode, int stages,
+                 int tma_rows) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], done_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int stage_bytes = 32768;
+  for (int i = threadIdx.x; i < (stages * stage_bytes) / 4; i += 128) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 2 && (mode & 4)) {
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(&empty_bar[st], ph ^ 1u);
+        mbar_expect_tx(&full_bar[st], (uint32_t)(tma_rows * 128));
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                         smem_u32(sm + st * stage_bytes)),
+                     "l"(reinterpret_cast<uint64_t>(&tmG)), "r"(smem_u32(&full_bar[st])), "r"(0), "r"((g * tma_rows) & 0xFFFF)
+                     : "memory");
+        if (++st == stages) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(128, N, 0, 0);
+    const uint64_t ad0 = umma_desc_sw128(base, 16, 1024), bd0 = umma_desc_sw128(base + 16384, 16, 1024);
+    long long t0 = clock64();
+    int st = 0; uint32_t ph = 0;
+    for (int g = 0; g < groups; ++g) {
+      if (mode & 4) { mbar_wait(&full_bar[st], ph); tc_fence_after(); }
+      else if ((mode & 2) && g >= stages) { mbar_wait(&empty_bar[st], ph ^ 1u); tc_fence_after(); }   // completed by the commit `stages` groups ago
+      if (elect_one()) {
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)(st * stage_bytes) >> 4), bd = bd0 + (uint64_t)((uint32_t)(st * stage_bytes) >> 4);
+        if (per == 8) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) umma_bf16(tmem + (uint32_t)((m & 1) * N), ad + 2 * (m & 3), bd + 2 * (m & 3), idesc, 1u);
+        } else {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) umma_bf16(tmem + (uint32_t)((m & 1) * N), ad + 2 * (m & 3), bd + 2 * (m & 3), idesc, 1u);
+        }
+        if (mode & 1) umma_commit(&empty_bar[st]);
+      }
+      __syncwarp();
+      if (++st == stages) { st = 0; ph ^= 1u; }
+    }
+    if (elect_one()) umma_commit(&done_bar);
+    __syncwarp();
+    mbar_wait(&done_bar, 0);
+    if (lane == 0) out[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem, 512); }
+}
+
 }  // namespace
+
+extern "C" int awr_debug_umma_pipe(const void* G, int g_rows, unsigned long long* out_dev, int N, int per, int groups, int mode, int stages,
+                                   int tma_rows, int grid, void* stream) {
+  AWR_HOST_CHECK(G && out_dev && N >= 16 && 2 * N <= 512 && per > 0 && groups > 0 && stages >= 1 && stages <= 6 && tma_rows <= 256 && tma_rows > 0);
+  CUtensorMap tmG;
+  const long long dims[2] = {64, g_rows}, str[2] = {1, 64};
+  const int box[2] = {64, tma_rows};
+  if (!make_tmap_bf16(&tmG, G, 2, dims, str, box, nullptr)) return AWR_ERR_DRIVER;
+  const size_t smem = (size_t)stages * 32768 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(umma_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  umma_pipe_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(tmG, out_dev, N, per, groups, mode, stages, tma_rows);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+extern "C" int awr_debug_umma_rate(unsigned long long* out_dev, int N, int nacc, int iters, int a_rows_shift, int grid, void* stream) {
+  AWR_HOST_CHECK(out_dev && N >= 16 && N <= 256 && nacc >= 1 && nacc * N <= 512 && iters > 0 && grid > 0);
+  const size_t smem = 49 * 1024 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  umma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(out_dev, N, nacc, iters, a_rows_shift);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
 
 extern "C" int awr_debug_umma_window(const void* G, const void* Bm, float* D, int rows, int r0, int sbo_rows, int base_mode, void* stream) {
   AWR_HOST_CHECK(G && Bm && D && rows >= 128 && rows <= 256 && r0 >= 0 && sbo_rows >= 8);

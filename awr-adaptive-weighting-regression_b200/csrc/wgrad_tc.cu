@@ -2,13 +2,19 @@
 //
 //   dW[tap][i*s_p + j*s_g] += sum over coarse pixels q of  pointwise[q, i] * gathered[q*stride - pad + tap, j]
 //
-// as a GEMM whose contraction dimension is the PIXEL index:  D[m = gathered channel j (of tap t)][n = pointwise channel i].
-// Both operands are read straight from the NHWC tensors by TMA boxes of (64 channels x 64 pixels) and consumed as
-// MN-major UMMA operands (the channel dimension is contiguous in memory, the pixel dimension strides by 128 B in smem),
-// so no transposed copy of the activations is ever made.  The gathered operand's box is shifted by the tap offset
-// (zero OOB fill = padding) and strided by the tensor map's element strides for stride-2 layers.
-// M tile = 128 = two 64-channel blocks: two different taps when the gathered tensor has 64 channels, else two channel
-// blocks of one tap.  The pixel range is split across CTAs (split-K); partial tiles are combined with fp32 red.global.add.
+// as a GEMM whose contraction dimension is the PIXEL index:  D[m = (tap, gathered channel j)][n = pointwise channel i].
+// Both operands are consumed as MN-major UMMA operands straight from TMA boxes of the NHWC tensors (channels contiguous,
+// pixels stride 128 B in smem) -- no transposed copy of any activation exists.
+//
+// Operand reuse (the per-SM L2 port, ~64 B/clk, is the binding resource -- DESIGN.md section 8): a CTA owns a GROUP of taps
+// that share one halo patch of the gathered tensor per 64-pixel block (8x8 coarse pixels): UMMA applies the 128-B swizzle on
+// absolute smem address bits, so each tap is just a row-shifted window (start = halo + ((dy*PW + dx) * 128 B), K-group stride
+// SBO = PW * 128 B) of the same TMA-written tile, and ONE pointwise tile feeds every tap of the group.  Groups: all taps of a
+// stride-1 conv when they fit TMEM (Cin = 64: five M tiles of two taps each), one tap row otherwise; for stride-2 layers the
+// taps of one parity class (their gathers are unit shifts of the same stride-2 sub-grid, loaded with TMA element strides).
+// M tile = 128 rows = two 64-channel blocks (two taps of a 64-channel tensor, or two channel blocks of one tap) stitched by the
+// descriptor's leading-dimension offset.  Accumulators: n_mtiles x Ntile fp32 TMEM columns (<= 512), one pass per CTA; the
+// pixel range is split across CTAs (split-K) and partial tiles are combined with fp32 red.global.add.
 //
 // Replaces the weight part of autograd's convolution_backward for model/resnet_deconv.py and model/hourglass.py layers
 // in the bf16 precision mode.  Same argument meaning as awr_conv_wgrad_simt.
@@ -20,119 +26,145 @@ namespace {
 using namespace tc;
 
 constexpr int kThreads = 192;
-constexpr int kABytes = 128 * 128;   // 2 blocks x (64 pixels x 64 ch bf16)
+constexpr int kMaxMTiles = 5;
+constexpr int kMaxGroups = 9;
 
-struct WgradTcParams {
-  int N, Hc, Wc;                     // coarse grid (pointwise tensor)
-  int Wt, Ht, Nt, tiles_w, tiles_h, tiles_nb, pix_blocks;   // 64-pixel K blocks
-  int Cp, Cg, Ntile, tiles_n;        // pointwise channels (GEMM N), gathered channels (GEMM M)
-  int m_items;                       // tap slots (Cg == 64: pairs of taps) or taps x Cg/128
-  int R, S, stride, pad;
-  int s_p, s_g, w_tap;
-  int ksplit, stages;
+struct MTile {
+  int tap[2];            // weight tap of each 64-row block
+  int ch[2];             // gathered-channel offset (within the CTA's channel block) of each 64-row block
+  int aoff[2];           // byte offset of each block's window inside the stage's halo region
+  int valid1;            // second block carries real data
+};
+struct TapGroup {
+  int n_mtiles, halo_ox, halo_oy, pw, hrows;
+  MTile mt[kMaxMTiles];
+};
+
+struct WgradParams {
+  int N, Hc, Wc, tiles_w, tiles_h, pix_blocks, Wt, Ht, Nt;   // coarse grid in 64-pixel blocks (8x8x1, or whole small maps x Nt images)
+  int Cp, Cg, Ntile, tiles_n, cg_blocks, halo_blocks; // halo_blocks: 64-channel TMA boxes of the gathered tensor per k-block (1 or 2)
+  int stride, s_p, s_g, w_tap;
+  int ksplit, stages, halo_block_bytes, stage_bytes;
+  int ngroups;
+  TapGroup grp[kMaxGroups];
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmP, float* __restrict__ dW,
-                const __grid_constant__ WgradTcParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1, const __grid_constant__ CUtensorMap tmG2,
+                const __grid_constant__ CUtensorMap tmG3, const __grid_constant__ CUtensorMap tmP, float* __restrict__ dW,
+                const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stage_bytes = kABytes + p.Ntile * 128;
+  uint8_t* const smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  // work item of this CTA
+  // work item of this CTA: (tap group, gathered-channel block, pointwise-channel tile, pixel range)
   int item = blockIdx.x;
   const int ks = item % p.ksplit; item /= p.ksplit;
-  const int nt = item % p.tiles_n; const int mi = item / p.tiles_n;
-  const int T = p.R * p.S;
-  int tap[2], ch0[2];
-  if (p.Cg == 64) { tap[0] = 2 * mi; tap[1] = 2 * mi + 1; ch0[0] = ch0[1] = 0; }
-  else { const int cb = p.Cg / 128; tap[0] = tap[1] = mi / cb; ch0[0] = (mi % cb) * 128; ch0[1] = ch0[0] + 64; }
-  const bool blk1_valid = tap[1] < T;
-  if (!blk1_valid) tap[1] = tap[0];
+  const int nt = item % p.tiles_n; item /= p.tiles_n;
+  const int cgb = item % p.cg_blocks; const int gi = item / p.cg_blocks;
+  const TapGroup& G = p.grp[gi];
+  const int cg0 = cgb * 64 * p.halo_blocks;
   const int per = (p.pix_blocks + p.ksplit - 1) / p.ksplit;
   const int pb0 = ks * per, pb1 = min(p.pix_blocks, pb0 + per);
   const int iters = max(pb1 - pb0, 0);
+  const int hbytes = G.pw * G.hrows * 128;
+  // the gathered tensor map of this group (box shape depends on the group's halo extents): groups are numbered so that
+  // groups with equal box shape share a map index (host fills map_of_group in halo_ox's upper bits -> kept simple: gi & 3)
+  const CUtensorMap* tmG = (gi & 3) == 0 ? &tmG0 : ((gi & 3) == 1 ? &tmG1 : ((gi & 3) == 2 ? &tmG2 : &tmG3));
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(tmG);
     tma_prefetch_desc(&tmP);
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tfull_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 5) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == 0) {
+  if (warp == 4) {
+    // ======================================= TMA producer =======================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(p.halo_blocks * hbytes + p.Ntile * 128);
       for (int pb = pb0; pb < pb1; ++pb) {
         const int tw = pb % p.tiles_w; int r = pb / p.tiles_w;
-        const int th = r % p.tiles_h; const int tn = r / p.tiles_h;
-        const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt;
+        const int th = r % p.tiles_h; const int n = (r / p.tiles_h) * p.Nt;
+        const int w0 = tw * p.Wt, h0 = th * p.Ht;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-        uint8_t* sa = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes;
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int tr = tap[b] / p.S, ts = tap[b] % p.S;
-          tma_load_4d(sa + b * 8192, &tmG, &full_bar[stage], ch0[b], w0 * p.stride - p.pad + ts, h0 * p.stride - p.pad + tr, n0);
-        }
-        uint8_t* sb = sa + kABytes;
-        for (int j = 0; j < p.Ntile / 64; ++j) tma_load_4d(sb + j * 8192, &tmP, &full_bar[stage], nt * p.Ntile + 64 * j, w0, h0, n0);
+        mbar_expect_tx(&full_bar[stage], tx);
+        uint8_t* sa = smem_al + (size_t)stage * p.stage_bytes;
+        for (int b = 0; b < p.halo_blocks; ++b)
+          tma_load_4d(sa + b * p.halo_block_bytes, tmG, &full_bar[stage], cg0 + 64 * b, w0 * p.stride + G.halo_ox, h0 * p.stride + G.halo_oy, n);
+        uint8_t* sb = sa + p.halo_blocks * p.halo_block_bytes;
+        for (int j = 0; j < p.Ntile / 64; ++j) tma_load_4d(sb + j * 8192, &tmP, &full_bar[stage], nt * p.Ntile + 64 * j, w0, h0, n);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.Ntile, 1, 1);
-      int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)(stage * stage_bytes), sb = sa + kABytes;
+  } else if (warp == 5) {
+    // ======================================= MMA issuer =======================================
+    const uint32_t idesc = umma_idesc_bf16(128, p.Ntile, 1, 1);
+    const uint32_t sbo = (uint32_t)G.pw * 128u;                         // stride between 8-pixel K groups (one halo row)
+    const uint32_t kstep = (2u * sbo) >> 4;                             // UMMA_K = 16 pixels = two halo rows
+    const uint32_t b_off = (uint32_t)(p.halo_blocks * p.halo_block_bytes);
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+        const uint64_t bd = umma_desc_sw128(sa + b_off, 8192, 1024);
+        for (int m = 0; m < G.n_mtiles; ++m) {
+          const MTile& T = G.mt[m];
+          const uint64_t ad = umma_desc_sw128(sa + (uint32_t)T.aoff[0], (uint32_t)(T.aoff[1] - T.aoff[0]), sbo);
+          const uint32_t d = tmem_base + (uint32_t)(m * p.Ntile);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = umma_desc_sw128(sa + k * 2048, 8192, 1024);
-          const uint64_t bd = umma_desc_sw128(sb + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_bf16(d, ad + (uint64_t)(k * kstep), bd + (uint64_t)(k * 128), idesc, (it | k) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+    if (elect_one()) {
       if (iters > 0) umma_commit(&tfull_bar);
       else mbar_arrive(&tfull_bar);
     }
+    __syncwarp();
   } else {
+    // ======================================= epilogue =======================================
     const int q = warp & 3;
     const int row = q * 32 + lane, blk = row >> 6, j = row & 63;
-    const bool valid = (blk == 0 || blk1_valid) && iters > 0;
-    float* base = dW + (size_t)tap[blk] * p.w_tap + (size_t)(ch0[blk] + j) * p.s_g + (size_t)(nt * p.Ntile) * p.s_p;
     mbar_wait(&tfull_bar, 0);
     tc_fence_after();
     if (iters > 0) {
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int ch = 0; ch < p.Ntile; ch += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + ch, v);
-        tmem_ld_wait();
-        if (valid) {
+      for (int m = 0; m < G.n_mtiles; ++m) {
+        const MTile& T = G.mt[m];
+        const bool valid = (blk == 0 || T.valid1);
+        float* base = dW + (size_t)T.tap[blk] * p.w_tap + (size_t)(cg0 + T.ch[blk] + j) * p.s_g + (size_t)(nt * p.Ntile) * p.s_p;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * p.Ntile);
+        for (int ch = 0; ch < p.Ntile; ch += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + ch, v);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(base + (size_t)(ch + i) * p.s_p, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; ++i) atomicAdd(base + (size_t)(ch + i) * p.s_p, __uint_as_float(v[i]));
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 5) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace
@@ -142,54 +174,133 @@ extern "C" {
 int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
                       int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream) {
   AWR_HOST_CHECK(pointwise && gathered && dW && N > 0 && Cp % 64 == 0 && Cg % 64 == 0 && (Cg == 64 || Cg % 128 == 0));
-  AWR_HOST_CHECK(R > 0 && S > 0 && (stride == 1 || stride == 2));
+  AWR_HOST_CHECK(R > 0 && S > 0 && R * S <= 16 && (stride == 1 || stride == 2));
   AWR_HOST_CHECK(is_pow2(Wc) && is_pow2(Hc) && Wc <= 256 && Hc <= 256);
-  WgradTcParams p;
+  WgradParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.Hc = Hc; p.Wc = Wc;
-  p.Wt = Wc < 64 ? Wc : 64;
-  p.Ht = (64 / p.Wt) < Hc ? (64 / p.Wt) : Hc;
-  p.Nt = 64 / (p.Wt * p.Ht);
-  p.tiles_w = Wc / p.Wt; p.tiles_h = Hc / p.Ht; p.tiles_nb = (N + p.Nt - 1) / p.Nt;
-  p.pix_blocks = p.tiles_w * p.tiles_h * p.tiles_nb;
-  p.Cp = Cp; p.Cg = Cg;
-  p.Ntile = (Cp % 256 == 0) ? 256 : ((Cp % 128 == 0) ? 128 : 64);
+  p.Cp = Cp; p.Cg = Cg; p.stride = stride; p.s_p = s_p; p.s_g = s_g; p.w_tap = w_tap;
+  p.halo_blocks = (Cg == 64) ? 1 : 2;
+  p.cg_blocks = Cg / (64 * p.halo_blocks);
+  p.Ntile = (Cp % 128 == 0) ? 128 : 64;
   p.tiles_n = Cp / p.Ntile;
-  const int T = R * S;
-  p.m_items = (Cg == 64) ? (T + 1) / 2 : T * (Cg / 128);
-  p.R = R; p.S = S; p.stride = stride; p.pad = pad;
-  p.s_p = s_p; p.s_g = s_g; p.w_tap = w_tap;
-  const int base_items = p.m_items * p.tiles_n;
-  int ksplit = (2 * 148 + base_items - 1) / base_items;
-  if (ksplit > p.pix_blocks) ksplit = p.pix_blocks;
-  if (ksplit < 1) ksplit = 1;
-  p.ksplit = ksplit;
-  const int stage_bytes = kABytes + p.Ntile * 128;
-  p.stages = (200 * 1024) / stage_bytes;
-  if (p.stages > 8) p.stages = 8;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const int max_mt = 512 / p.Ntile < kMaxMTiles ? 512 / p.Ntile : kMaxMTiles;
 
-  CUtensorMap tmG, tmP;
-  {
+  // ---- pixel blocks: 8x8 coarse pixels of one image; smaller maps use the whole map of several images -------------------
+  // (maps below 8x8 keep the 64-pixel K block by taking Wt x Ht x Nt = 64 with Nt images; no halo sharing across images is
+  //  needed because each image's halo rows are separate TMA box slices -> handled by treating them as 1-tap groups)
+  const bool small = (Wc < 8 || Hc < 8);
+  const int Wt = small ? Wc : 8, Ht = small ? Hc : 8, Nt = 64 / (Wt * Ht);
+  p.Wt = Wt; p.Ht = Ht; p.Nt = Nt;
+  p.tiles_w = Wc / Wt; p.tiles_h = Hc / Ht;
+  p.pix_blocks = p.tiles_w * p.tiles_h * ((N + Nt - 1) / Nt);
+
+  // ---- tap groups ------------------------------------------------------------------------------------------------------
+  struct TapI { int r, s, oy, ox; };
+  TapI cls[4][16]; int ncls[4] = {0, 0, 0, 0};
+  const int nclass = stride * stride;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      // gathered pixel = q*stride - pad + (r,s): parity class of the tap and its unit shift inside the stride-sub-grid
+      const int ty = r - pad, tx = s - pad;
+      const int cy = ((ty % stride) + stride) % stride, cx = ((tx % stride) + stride) % stride;
+      const int c = cy * stride + cx;
+      cls[c][ncls[c]++] = TapI{r, s, (ty - cy) / stride, (tx - cx) / stride};
+    }
+  int ng = 0;
+  int map_box[4][2]; int nmaps = 0;            // distinct (pw, hrows) box shapes -> at most 4 tensor maps
+  int group_cls[kMaxGroups];
+  for (int c = 0; c < nclass; ++c) {
+    if (ncls[c] == 0) continue;
+    // taps per group: as many as fit TMEM; groups are cut at tap-row boundaries when a whole class does not fit
+    const int taps_per_mt = (Cg == 64) ? 2 : 1;
+    int start = 0;
+    while (start < ncls[c]) {
+      int end = ncls[c];
+      if (small) end = start + 1;
+      else if ((end - start + taps_per_mt - 1) / taps_per_mt > max_mt) {
+        end = start;                              // take whole tap rows while they fit
+        while (end < ncls[c]) {
+          int e2 = end; const int row_r = cls[c][end].r;
+          while (e2 < ncls[c] && cls[c][e2].r == row_r) ++e2;
+          if ((e2 - start + taps_per_mt - 1) / taps_per_mt > max_mt) break;
+          end = e2;
+        }
+        if (end == start) end = start + taps_per_mt * max_mt < ncls[c] ? start + taps_per_mt * max_mt : ncls[c];
+      }
+      AWR_HOST_CHECK(ng < kMaxGroups);
+      TapGroup& G = p.grp[ng];
+      int mnx = 99, mxx = -99, mny = 99, mxy = -99;
+      for (int i = start; i < end; ++i) { mnx = min(mnx, cls[c][i].ox); mxx = max(mxx, cls[c][i].ox); mny = min(mny, cls[c][i].oy); mxy = max(mxy, cls[c][i].oy); }
+      G.pw = Wt + (mxx - mnx); G.hrows = Ht * Nt + (mxy - mny);   // small maps: Nt > 1 only with a single tap (no extents)
+      const int cy = c / stride, cx = c % stride;
+      G.halo_ox = mnx * stride + cx; G.halo_oy = mny * stride + cy;
+      const int hb = G.pw * G.hrows * 128;
+      if (hb > p.halo_block_bytes) p.halo_block_bytes = hb;
+      int m = 0;
+      for (int i = start; i < end; i += taps_per_mt) {
+        MTile& T = G.mt[m++];
+        const int o0 = ((cls[c][i].oy - mny) * G.pw + (cls[c][i].ox - mnx)) * 128;
+        T.tap[0] = cls[c][i].r * S + cls[c][i].s; T.aoff[0] = o0; T.ch[0] = 0;
+        if (taps_per_mt == 2) {
+          if (i + 1 < end) {
+            T.tap[1] = cls[c][i + 1].r * S + cls[c][i + 1].s;
+            T.aoff[1] = ((cls[c][i + 1].oy - mny) * G.pw + (cls[c][i + 1].ox - mnx)) * 128; T.ch[1] = 0; T.valid1 = 1;
+          } else { T.tap[1] = T.tap[0]; T.aoff[1] = o0; T.ch[1] = 0; T.valid1 = 0; }
+        } else { T.tap[1] = T.tap[0]; T.aoff[1] = -1; T.ch[1] = 64; T.valid1 = 1; }   // second channel block: fixed up below
+      }
+      G.n_mtiles = m;
+      group_cls[ng] = c;
+      ++ng;
+      start = end;
+    }
+  }
+  p.ngroups = ng;
+  p.halo_block_bytes = (p.halo_block_bytes + 1023) & ~1023;
+  for (int g = 0; g < ng; ++g)
+    for (int m = 0; m < p.grp[g].n_mtiles; ++m)
+      if (p.grp[g].mt[m].aoff[1] < 0) p.grp[g].mt[m].aoff[1] = p.grp[g].mt[m].aoff[0] + p.halo_block_bytes;
+  (void)group_cls;
+
+  // ---- tensor maps: one per group slot (gi & 3); groups beyond 4 must repeat the box shape of group gi-4 ---------------
+  CUtensorMap tmG[4], tmP;
+  for (int g = 0; g < 4; ++g) {
+    const TapGroup& G = p.grp[g < ng ? g : 0];
     const long long dims[4] = {Cg, Wf, Hf, N};
     const long long str[4] = {1, Cg, (long long)Wf * Cg, (long long)Hf * Wf * Cg};
-    const int box[4] = {64, p.Wt * stride, p.Ht * stride, p.Nt};
-    const int es[4] = {1, stride, stride, 1};
-    if (!make_tmap_bf16(&tmG, gathered, 4, dims, str, box, es)) return AWR_ERR_DRIVER;
+    int box[4], es[4] = {1, stride, stride, 1};
+    if (!small) { box[0] = 64; box[1] = G.pw * stride; box[2] = G.hrows * stride; box[3] = 1; }
+    else { box[0] = 64; box[1] = Wt * stride; box[2] = Ht * stride; box[3] = Nt; }
+    AWR_HOST_CHECK(box[1] <= 256 && box[2] <= 256);
+    if (!make_tmap_bf16(&tmG[g], gathered, 4, dims, str, box, es)) return AWR_ERR_DRIVER;
   }
+  for (int g = 4; g < ng; ++g) AWR_HOST_CHECK(p.grp[g].pw == p.grp[g - 4].pw && p.grp[g].hrows == p.grp[g - 4].hrows);
+  if (small) for (int g = 0; g < ng; ++g) { p.grp[g].pw = 8; p.grp[g].hrows = 8; }   // dense 64-row block: K groups are consecutive 8-row atoms
   {
     const long long dims[4] = {Cp, Wc, Hc, N};
     const long long str[4] = {1, Cp, (long long)Wc * Cp, (long long)Hc * Wc * Cp};
-    const int box[4] = {64, p.Wt, p.Ht, p.Nt};
+    const int box[4] = {64, Wt, Ht, Nt};
     if (!make_tmap_bf16(&tmP, pointwise, 4, dims, str, box, nullptr)) return AWR_ERR_DRIVER;
   }
+  p.stage_bytes = p.halo_blocks * p.halo_block_bytes + p.Ntile * 128;
+  p.stages = (200 * 1024) / p.stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  AWR_HOST_CHECK(p.stages >= 2);
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+
+  const int base_items = ng * p.cg_blocks * p.tiles_n;
+  int ksplit = 148 / base_items;                       // whole waves: never more CTAs than SMs unless the base grid already exceeds them
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > p.pix_blocks) ksplit = p.pix_blocks;
+  p.ksplit = ksplit;
+
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  wgrad_tc_kernel<<<base_items * ksplit, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmP, dW, p);
+  wgrad_tc_kernel<<<base_items * ksplit, kThreads, smem, (cudaStream_t)stream>>>(tmG[0], tmG[1], tmG[2], tmG[3], tmP, dW, p);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

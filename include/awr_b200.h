@@ -164,6 +164,11 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
 /* ---- debug / hardware probes (not on the product path) -------------------------------------------------------------- */
 /* D[128][64] fp32 = A * Bm^T where A is the row-shifted window {r0 + (m/8)*sbo_rows + m%8} of the TMA-loaded smem tile G[rows][64]
  * (bf16, SWIZZLE_128B); probes UMMA descriptor start-address / SBO / base-offset semantics (tools/dbg_umma_window.py). */
+/* MMA issue/execute rate: out_dev[grid] cycles for iters*4 tcgen05.mma (M=128,N,K=16) over nacc accumulators (tools/dbg_umma_rate.py). */
+int awr_debug_umma_rate(unsigned long long* out_dev, int N, int nacc, int iters, int a_rows_shift, int grid, void* stream);
+/* MMA-issuer loop probe: commit / barrier-wait / TMA-fed ring overheads per group of `per` MMAs (tools/dbg_umma_rate.py). */
+int awr_debug_umma_pipe(const void* G, int g_rows, unsigned long long* out_dev, int N, int per, int groups, int mode, int stages,
+                        int tma_rows, int grid, void* stream);
 int awr_debug_umma_window(const void* G, const void* Bm, float* D, int rows, int r0, int sbo_rows, int base_mode, void* stream);
 
 #ifdef __cplusplus

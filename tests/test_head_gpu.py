@@ -91,7 +91,7 @@ def test_head_full_size_properties():
     FM = awr_b200.FeatureModule()
     gt = FM.joint2offset(jt, img, 1.0, Fs)
     uvd, loss, _ = head_loss_forward(gt, img, jt, 1.0)
-    assert loss[1].item() == 0.0                       # pred == GT volume -> dense loss exactly 0
+    assert loss[1].item() < 1e-12                      # pred == GT volume -> dense loss 0 up to FMA-contraction differences between kernels
     # every contributing pixel votes exactly for the joint: val = off_n*dis + coord = joint wherever the mask is 1
     assert (uvd - jt).abs().max().item() < 0.12
     # linearity in the offset planes for fixed heat-maps: uvd(2*vec) - uvd(vec) == uvd(vec) - uvd(0*vec)

@@ -63,6 +63,9 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
 
+// value as it reads back after being stored in T (bf16 rounding; identity for float)
+template <typename T> __device__ __forceinline__ float from_store(float v) { return to_f<T>(from_f<T>(v)); }
+
 // 8-wide channel vector load/store (NHWC, C % 8 == 0): fp32 -> 2x float4, bf16 -> 1x uint4
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {

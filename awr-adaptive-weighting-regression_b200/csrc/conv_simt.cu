@@ -313,6 +313,78 @@ __global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __re
   }
 }
 
+// Register-tiled stem convolution: thread = 4 consecutive pixels of a row x 8 output channels (32 accumulators); the 5 x 8 input
+// patch is read once per thread and every weight vector fetched from shared memory feeds 4 pixels.  Optionally accumulates the
+// BatchNorm batch statistics (per-channel sum / sum of squares of the stored values) so no separate reduction pass is needed.
+template <typename T, int K>
+__global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                              T* __restrict__ y, float* __restrict__ stats, int N, int H, int W, int Cout) {
+  extern __shared__ __align__(16) float ws[];   // [K*K][Cout] then reduction scratch
+  for (int i = threadIdx.x; i < K * K * Cout; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  constexpr int PADK = K / 2, XS = 4 + K - 1;
+  const int G = Cout >> 3, W4 = W >> 2;
+  const long long items = (long long)N * H * W4 * G, stride = (long long)gridDim.x * blockDim.x;
+  const int cg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % G);
+  float s1[8] = {}, s2[8] = {};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+    long long t = i / G;
+    const int w4 = (int)(t % W4); t /= W4;
+    const int hy = (int)(t % H);
+    const int n = (int)(t / H);
+    const int wx = w4 * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int p4 = 0; p4 < 4; ++p4)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[p4][q] = bias ? bias[cg * 8 + q] : 0.f;
+    const float* xi = x + (long long)n * H * W;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int hh = hy + r - PADK;
+      if (hh < 0 || hh >= H) continue;
+      float xs[XS];
+#pragma unroll
+      for (int c = 0; c < XS; ++c) {
+        const int ww = wx + c - PADK;
+        xs[c] = (ww >= 0 && ww < W) ? __ldg(xi + (long long)hh * W + ww) : 0.f;
+      }
+#pragma unroll
+      for (int s2_ = 0; s2_ < K; ++s2_) {
+        const float4 wa = *reinterpret_cast<const float4*>(ws + (r * K + s2_) * Cout + cg * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(ws + (r * K + s2_) * Cout + cg * 8 + 4);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int p4 = 0; p4 < 4; ++p4)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[p4][q] = fmaf(xs[p4 + s2_], wv[q], acc[p4][q]);
+      }
+    }
+#pragma unroll
+    for (int p4 = 0; p4 < 4; ++p4) {
+      Vec8<T>::store(y + ((((long long)n * H + hy) * W + wx + p4) * G + cg) * 8, acc[p4]);
+      if (stats) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const float v = from_store<T>(acc[p4][q]); s1[q] += v; s2[q] += v * v; }
+      }
+    }
+  }
+  if (stats) {
+    // threads with equal (threadIdx % G) share a channel octet: reduce over them in shared memory, one atomic per channel per block
+    __syncthreads();
+    float* red = ws;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { red[threadIdx.x * 16 + q] = s1[q]; red[threadIdx.x * 16 + 8 + q] = s2[q]; }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < 2 * Cout; ch += blockDim.x) {
+      const int which = ch / Cout, c = ch % Cout, g = c >> 3, q = c & 7;
+      float sum = 0.f;
+      for (int r = g; r < (int)blockDim.x; r += G) sum += red[r * 16 + which * 8 + q];
+      atomicAdd(stats + which * Cout + c, sum);
+    }
+  }
+}
+
 }  // namespace
 
 #define DISPATCH_T(dtype, ...)                                             \
@@ -352,9 +424,20 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, 
   return AWR_OK;
 }
 
-int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout, int k,
+int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, float* stats, int dtype, int N, int H, int W, int Cout, int k,
                   void* stream) {
   AWR_HOST_CHECK(x && w && y && N > 0 && Cout % 8 == 0 && k % 2 == 1 && k <= 7);
+  if (k == 5 && W % 4 == 0 && (256 % (Cout / 8)) == 0) {
+    const long long items4 = (long long)N * H * (W / 4) * (Cout / 8);
+    long long blocks4 = (items4 + 255) / 256;
+    if (blocks4 > 148 * 8) blocks4 = 148 * 8;
+    size_t smem4 = (size_t)k * k * Cout * sizeof(float);
+    if (smem4 < 256 * 16 * sizeof(float)) smem4 = 256 * 16 * sizeof(float);
+    DISPATCH_T(dtype, stem_conv_tiled_kernel<T, 5><<<(int)blocks4, 256, smem4, (cudaStream_t)stream>>>(x, w, bias, (T*)y, stats, N, H, W, Cout));
+    AWR_LAUNCH_CHECK();
+    return AWR_OK;
+  }
+  AWR_HOST_CHECK(stats == nullptr);
   const long long items = (long long)N * H * W * (Cout / 8);
   long long blocks = (items + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -220,6 +220,202 @@ bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSe
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// fused stem tail of ResnetDeconv (resnet_deconv.py:33-35): BatchNorm + ReLU + MaxPool(k,s,p) read the raw conv output y ONCE and
+// write only the pooled tensor (+ arg-max tap byte); the full-resolution normalised tensor is never materialised.  Backward
+// (maxpool_bn_bwd_kernel) rebuilds d(relu(bn(y))) per full-resolution pixel from the pooled gradient + arg-max bytes (gather form,
+// at most 4 overlapping windows) and the ReLU mask from y itself, so neither that tensor nor its gradient ever exists in HBM.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+bn_relu_maxpool_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ out, unsigned char* __restrict__ idx, int N, int H, int W, int C,
+                           int Ho, int Wo, int k, int s, int p, float count, float momentum, float eps, int training) {
+  const int G = C >> 3;
+  const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
+  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { float mean, invstd, var; bn_coeffs(bn, c0 + q, C, count, eps, training, sc[q], sh[q], mean, invstd, var); }
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    unsigned char bi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bi[q] = 0; }
+    for (int r = 0; r < k; ++r) {
+      const int hi = ho * s - p + r;
+      if (hi < 0 || hi >= H) continue;
+      for (int c = 0; c < k; ++c) {
+        const int wi = wo * s - p + c;
+        if (wi < 0 || wi >= W) continue;
+        float v[8];
+        Vec8<T>::load(y + (((long long)n * H + hi) * W + wi) * C + c0, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a = from_store<T>(fmaxf(v[q] * sc[q] + sh[q], 0.f));      // the value the unfused path would have stored
+          if (a > best[q]) { best[q] = a; bi[q] = (unsigned char)(r * k + c); }
+        }
+      }
+    }
+    Vec8<T>::store(out + i * 8, best);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((unsigned)bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((unsigned)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1) { __syncthreads(); bn_side_effects(bn, C, count, momentum, eps, training); }
+}
+
+// pass 0: dsums[0:C] += sum dz, dsums[C:2C] += sum dz*yhat;   pass 1: dy = gamma*invstd*(dz - mean(dz) - yhat*mean(dz*yhat)), block 0
+// writes dgamma/dbeta.  dz[n,h,w,c] = (bn(y)>0) * sum over pooling windows containing (h,w) whose arg-max is (h,w) of dpool.
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restrict__ idx, const T* __restrict__ y,
+                      const float* __restrict__ mean_invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
+                      int C, int Ho, int Wo, int k, int s, int p, int pass, int accumulate_param_grads) {
+  __shared__ float smem[kEwThreads * 8];
+  const int G = C >> 3;
+  const long long items = (long long)N * H * W * G, stride = (long long)gridDim.x * kEwThreads;
+  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  const float invM = 1.0f / ((float)N * (float)H * (float)W);
+  float mean[8], istd[8], sc[8], sh[8], k1[8], k2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    mean[q] = mean_invstd[c0 + q]; istd[q] = mean_invstd[C + c0 + q];
+    sc[q] = gamma[c0 + q] * istd[q]; sh[q] = beta[c0 + q] - mean[q] * sc[q];
+    k1[q] = pass ? dsums[c0 + q] * invM : 0.f; k2[q] = pass ? dsums[C + c0 + q] * invM : 0.f;
+  }
+  float acc[2][8] = {};
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    long long t = i / G;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float yy[8], dz[8] = {};
+    Vec8<T>::load(y + i * 8, yy);
+    const int ho_lo = max(0, (h + p - k + 1 + s - 1) / s), ho_hi = min(Ho - 1, (h + p) / s);
+    const int wo_lo = max(0, (w + p - k + 1 + s - 1) / s), wo_hi = min(Wo - 1, (w + p) / s);
+    for (int ho = ho_lo; ho <= ho_hi; ++ho)
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const int tap = (h - (ho * s - p)) * k + (w - (wo * s - p));
+        const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + c0;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+        float g[8];
+        Vec8<T>::load(dpool + o, g);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const unsigned b = (q < 4) ? ((pk.x >> (8 * q)) & 0xffu) : ((pk.y >> (8 * (q - 4))) & 0xffu);
+          if ((int)b == tap) dz[q] += g[q];
+        }
+      }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dz[q] = (from_store<T>(fmaxf(yy[q] * sc[q] + sh[q], 0.f)) > 0.f) ? dz[q] : 0.f;
+    if (pass == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { acc[0][q] += dz[q]; acc[1][q] += dz[q] * (yy[q] - mean[q]) * istd[q]; }
+    } else {
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = sc[q] * (dz[q] - k1[q] - (yy[q] - mean[q]) * istd[q] * k2[q]);
+      Vec8<T>::store(dy + i * 8, o);
+    }
+  }
+  if (pass == 0) block_channel_reduce<2>(acc, G, C, dsums, smem);
+  else if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += kEwThreads) {
+      if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
+      else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
+    }
+  }
+}
+
+// MaxPool(3,2,1) specialisation of maxpool_bn_bwd_kernel (the ResNet stem): one thread owns a 2x2 block of full-resolution pixels
+// (x 8 channels); the four windows that can select any of them are loaded once and scattered with compile-time tap numbers.
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restrict__ idx, const T* __restrict__ y,
+                         const float* __restrict__ mean_invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         float* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
+                         int C, int pass, int accumulate_param_grads) {
+  __shared__ float smem[kEwThreads * 8];
+  const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
+  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  const float invM = 1.0f / ((float)N * (float)H * (float)W);
+  float mean[8], istd[8], sc[8], sh[8], k1[8], k2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    mean[q] = mean_invstd[c0 + q]; istd[q] = mean_invstd[C + c0 + q];
+    sc[q] = gamma[c0 + q] * istd[q]; sh[q] = beta[c0 + q] - mean[q] * sc[q];
+    k1[q] = pass ? dsums[c0 + q] * invM : 0.f; k2[q] = pass ? dsums[C + c0 + q] * invM : 0.f;
+  }
+  float acc[2][8] = {};
+  for (long long it = (long long)blockIdx.x * kEwThreads + threadIdx.x; it < items; it += stride) {
+    long long t = it / G;
+    const int j = (int)(t % Wo); t /= Wo;
+    const int i = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float dz[4][8] = {};
+    // windows (i+a, j+b), a,b in {0,1}: tap hit by block pixel (pr,pc) is (pr+1-2a)*3 + (pc+1-2b) when both factors are in [0,2]
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (i + a >= Ho || j + b >= Wo) continue;
+        const long long o = (((long long)n * Ho + i + a) * Wo + j + b) * C + c0;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+        float g[8];
+        Vec8<T>::load(dpool + o, g);
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc) {
+            const int r = pr + 1 - 2 * a, c = pc + 1 - 2 * b;
+            if (r < 0 || c < 0) continue;
+            const int tap = r * 3 + c;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const unsigned bb = (q < 4) ? ((pk.x >> (8 * q)) & 0xffu) : ((pk.y >> (8 * (q - 4))) & 0xffu);
+              if ((int)bb == tap) dz[pr * 2 + pc][q] += g[q];
+            }
+          }
+      }
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) {
+        const long long pix = (((long long)n * H + 2 * i + pr) * W + 2 * j + pc) * C + c0;
+        float yy[8];
+        Vec8<T>::load(y + pix, yy);
+        float* d = dz[pr * 2 + pc];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = (from_store<T>(fmaxf(yy[q] * sc[q] + sh[q], 0.f)) > 0.f) ? d[q] : 0.f;
+        if (pass == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { acc[0][q] += d[q]; acc[1][q] += d[q] * (yy[q] - mean[q]) * istd[q]; }
+        } else {
+          float o[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) o[q] = sc[q] * (d[q] - k1[q] - (yy[q] - mean[q]) * istd[q] * k2[q]);
+          Vec8<T>::store(dy + pix, o);
+        }
+      }
+  }
+  if (pass == 0) block_channel_reduce<2>(acc, G, C, dsums, smem);
+  else if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += kEwThreads) {
+      if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
+      else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // BN backward, pass 1: dz = dout * (act_out > 0 if relu);  dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * yhat
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -579,6 +775,38 @@ int awr_bn_act(const void* y, const float* sums, const float* gamma, const float
   BnSet b{res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
   DISPATCH_T(dtype, bn_act_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)y, a, (const T*)res, b, res_has_bn, (T*)out, M,
                                                                                              C, (float)M, momentum, eps, training, relu));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_bn_relu_maxpool_fwd(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            long long* num_batches_tracked, float* mean_invstd, void* out, unsigned char* idx, int dtype, int N, int H, int W,
+                            int C, int k, int s, int p, float momentum, float eps, int training, void* stream) {
+  AWR_HOST_CHECK(y && out && gamma && beta && N > 0 && chan_ok(C) && k >= 1 && k <= 3 && s >= 1);
+  AWR_HOST_CHECK(training ? (sums != nullptr) : (running_mean && running_var));
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
+  DISPATCH_T(dtype, bn_relu_maxpool_fwd_kernel<T><<<red_blocks((long long)N * Ho * Wo, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)y, a, (T*)out, idx, N, H, W, C, Ho, Wo, k, s, p, (float)((long long)N * H * W), momentum, eps, training));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* y, const float* mean_invstd, const float* gamma,
+                       const float* beta, float* dsums, void* dy, float* dgamma, float* dbeta, int dtype, int N, int H, int W, int C, int k,
+                       int s, int p, int pass, int accumulate_param_grads, void* stream) {
+  AWR_HOST_CHECK(dpool && idx && y && mean_invstd && gamma && beta && dsums && N > 0 && chan_ok(C) && (pass == 0 || dy != nullptr));
+  const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  if (k == 3 && s == 2 && p == 1 && H % 2 == 0 && W % 2 == 0) {
+    DISPATCH_T(dtype, maxpool3s2_bn_bwd_kernel<T><<<red_blocks((long long)N * Ho * Wo * 2, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+                          (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, dsums, (T*)dy, dgamma, dbeta, N, H, W, C, pass,
+                          accumulate_param_grads));
+    AWR_LAUNCH_CHECK();
+    return AWR_OK;
+  }
+  DISPATCH_T(dtype, maxpool_bn_bwd_kernel<T><<<red_blocks((long long)N * H * W, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+                        (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, dsums, (T*)dy, dgamma, dbeta, N, H, W, C, Ho, Wo, k, s, p,
+                        pass, accumulate_param_grads));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -154,9 +154,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(t_addr + ch, v);
           tmem_ld_wait();
-          if (valid) {
+          if (p.s_p != 1) {
+            // rows (gathered channels) are the contiguous dimension of dW: each column is one coalesced 128-B reduction per warp
+            if (valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(base + (size_t)(ch + i) * p.s_p, __uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i) atomicAdd(base + (size_t)(ch + i) * p.s_p, __uint_as_float(v[i]));
+            }
+          } else {
+            // columns (pointwise channels) are contiguous in dW (ConvTranspose2d layout): transpose the warp's 32x32 block through
+            // shared memory (the pipeline stages are idle by now) so every reduction instruction again covers one 128-B line
+            float* tb = reinterpret_cast<float*>(smem_al) + q * (32 * 33);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tb[lane * 33 + i] = __uint_as_float(v[i]);
+            __syncwarp();
+            const int r0 = q * 32;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int rw = r0 + rr, bk = rw >> 6, jj = rw & 63;
+              if (bk == 0 || T.valid1)
+                atomicAdd(dW + (size_t)T.tap[bk] * p.w_tap + (size_t)(cg0 + T.ch[bk] + jj) * p.s_g + (size_t)(nt * p.Ntile + ch + lane), tb[rr * 33 + lane]);
+            }
+            __syncwarp();
           }
         }
       }

@@ -315,6 +315,11 @@ class Plan:
         self.ops.append(op)
         return op.out
 
+    def bn_pool(self, y, prefix, k, s, p):
+        op = _BNPool(self, y, prefix, k, s, p)
+        self.ops.append(op)
+        return op.out
+
     def add(self, a, b, c=None):
         op = _Add(self, a, b, c)
         self.ops.append(op)
@@ -340,8 +345,7 @@ class Plan:
         kind, counts = RESNET_SPEC[layers]
         exp = 1 if kind == "basic" else 4
         y0 = self.stem("pre.0.weight", None, 64, 5)
-        a0 = self.bn_act(y0, "pre.1", True)
-        c = self.maxpool(a0, 3, 2, 1)
+        c = self.bn_pool(y0, "pre.1", 3, 2, 1)           # BN + ReLU + MaxPool(3,2,1) fused: the 128x128x64 normalised tensor is never stored
         inpl = 64
         for li, (planes, nblk) in enumerate(zip([64, 128, 256, 512], counts), start=1):
             for bi in range(nblk):
@@ -426,7 +430,9 @@ class _Stem(_Op):
         self.y = Act(plan, B, H, H, Cout)
         w = plan.P(wname)        # physical [k][k][Cout][1] == [k*k][Cout]
         b = plan.P(bname) if bname else None
-        plan.call(plan.fwd, "awr_stem_conv", plan.img, w, b, self.y.t, plan.dt, B, H, H, Cout, k)
+        if plan.training and k == 5:
+            self.y.stats = plan.arena(2 * Cout)          # BatchNorm statistics come out of the conv kernel itself
+        plan.call(plan.fwd, "awr_stem_conv", plan.img, w, b, self.y.t, self.y.stats, plan.dt, B, H, H, Cout, k)
 
     def plan_bwd(self):
         pl = self.plan
@@ -557,6 +563,33 @@ class _BNAct(_Op):
             pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, ry.t, self.bn_res.mi, self.bn_res.dsums, pl.P(rp + ".weight"), dry,
                     dry if ry.gw else None, None, None, pl.G(rp + ".weight"), pl.G(rp + ".bias"), pl.dt, ry.M, ry.C, 1)
             ry.gw = True
+
+
+class _BNPool(_Op):
+    """out = MaxPool(ReLU(BN(y)))  (resnet_deconv.py:33-35) without materialising the normalised tensor or its gradient."""
+
+    def __init__(self, plan, y, prefix, k, s, p):
+        self.plan, self.y, self.prefix, self.k, self.s, self.p = plan, y, prefix, k, s, p
+        pl, tr = plan, plan.training
+        self.bn = BNState(plan, prefix, y.C, y.stats)
+        Ho, Wo = (y.H + 2 * p - k) // s + 1, (y.W + 2 * p - k) // s + 1
+        self.out = Act(plan, y.N, Ho, Wo, y.C)
+        self.idx = torch.empty(y.N, Ho, Wo, y.C, dtype=torch.uint8, device=plan.device) if tr else None
+        if tr and not self.bn.fused_stats:
+            pl.call(pl.fwd, "awr_channel_stats", y.t, pl.dt, y.M, y.C, self.bn.sums, 1)
+        pl.call(pl.fwd, "awr_bn_relu_maxpool_fwd", y.t, self.bn.sums if tr else None, pl.P(prefix + ".weight"), pl.P(prefix + ".bias"),
+                pl.buf(prefix + ".running_mean"), pl.buf(prefix + ".running_var"), pl.buf(prefix + ".num_batches_tracked") if tr else None,
+                self.bn.mi, self.out.t, self.idx, pl.dt, y.N, y.H, y.W, y.C, k, s, p, BN_MOMENTUM, BN_EPS, int(tr))
+
+    def plan_bwd(self):
+        pl, y, out, pf = self.plan, self.y, self.out, self.prefix
+        if not out.gw:
+            return
+        assert not y.gw
+        for ps in (0, 1):
+            pl.call(pl.bwd, "awr_maxpool_bn_bwd", out.grad(), self.idx, y.t, self.bn.mi, pl.P(pf + ".weight"), pl.P(pf + ".bias"), self.bn.dsums,
+                    y.grad(), pl.G(pf + ".weight"), pl.G(pf + ".bias"), pl.dt, y.N, y.H, y.W, y.C, self.k, self.s, self.p, ps, 1)
+        y.gw = True
 
 
 class _Add(_Op):

@@ -81,6 +81,17 @@ int awr_bn_act(const void* y, const float* sums, const float* gamma, const float
                float* res_mean_invstd, void* out, int dtype, long long M, int C, float momentum, float eps, int training, int relu,
                void* stream);
 
+/* Fused stem tail (resnet_deconv.py:33-35): out = MaxPool_{k,s,p}(ReLU(BN(y))) read from the raw conv output in ONE pass; idx = arg-max
+ * tap byte per pooled element.  BN arguments as in awr_bn_act.  The full-resolution normalised tensor is never written. */
+int awr_bn_relu_maxpool_fwd(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            long long* num_batches_tracked, float* mean_invstd, void* out, unsigned char* idx, int dtype, int N, int H, int W,
+                            int C, int k, int s, int p, float momentum, float eps, int training, void* stream);
+/* Backward of the above straight to dy (gradient of the raw conv output): pass 0 accumulates dsums[2C] = {sum dz, sum dz*yhat} (caller
+ * zero-fills), pass 1 writes dy and dgamma/dbeta.  dz is rebuilt from dpool + idx (gather over <= 4 windows) and the ReLU mask from y. */
+int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* y, const float* mean_invstd, const float* gamma,
+                       const float* beta, float* dsums, void* dy, float* dgamma, float* dbeta, int dtype, int N, int H, int W, int C, int k,
+                       int s, int p, int pass, int accumulate_param_grads, void* stream);
+
 /* out = act( ss(y) + res_ss(res) ),  ss(v)[c] = v*scale[c] + shift[c]; scale_shift / res / res_scale_shift may be NULL. */
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream);
@@ -138,8 +149,9 @@ int awr_conv_simt(const void* in, const float* w, const float* bias, void* out, 
 int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, int dtype, int N, int Hc, int Wc, int Cp, int Hf, int Wf,
                         int Cg, int R, int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
 
-/* 1-channel k x k stride-1 'same' stem convolution: x (N,H,W) fp32, w [k*k][Cout] fp32, bias or NULL -> y NHWC. */
-int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, int dtype, int N, int H, int W, int Cout, int k,
+/* 1-channel k x k stride-1 'same' stem convolution: x (N,H,W) fp32, w [k*k][Cout] fp32, bias or NULL -> y NHWC.
+ * stats (or NULL; k = 5 only): fp32 [2*Cout] += per-channel sum / sum of squares of the stored outputs (BatchNorm statistics). */
+int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, float* stats, int dtype, int N, int H, int W, int Cout, int k,
                   void* stream);
 /* dW[k*k][Cout] += ..., dbias[Cout] += ... (dbias may be NULL); caller zero-fills. */
 int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int dtype, int N, int H, int W, int Cout, int k,

@@ -421,20 +421,27 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
-                     const float* __restrict__ mean_invstd, long long M, int C, float* __restrict__ dsums) {
+                     const float* __restrict__ mean_invstd, long long M, int C, float* __restrict__ dsums,
+                     const float* __restrict__ mask_gamma, const float* __restrict__ mask_beta) {
   __shared__ float smem[kEwThreads * 8];
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
-  float mean[8], istd[8];
+  float mean[8], istd[8], msc[8], msh[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k]; }
+  for (int k = 0; k < 8; ++k) {
+    mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k];
+    if (mask_gamma) { msc[k] = mask_gamma[c0 + k] * istd[k]; msh[k] = mask_beta[c0 + k] - mean[k] * msc[k]; }
+  }
   float acc[2][8] = {};
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
     float g[8], yy[8];
     Vec8<T>::load(dout + i * 8, g);
     Vec8<T>::load(y + i * 8, yy);
-    if (act_out) {
+    if (mask_gamma) {            // ReLU(BN(y)) without residual: the mask is a function of y alone, no need to read the activation
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = (from_store<T>(fmaxf(yy[k] * msc[k] + msh[k], 0.f)) > 0.f) ? g[k] : 0.f;
+    } else if (act_out) {
       float a[8];
       Vec8<T>::load(act_out + i * 8, a);
 #pragma unroll
@@ -453,22 +460,26 @@ __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
                     const float* __restrict__ mean_invstd, const float* __restrict__ dsums, const float* __restrict__ gamma,
                     T* dy, const T* dy_addend, T* dres, const T* dres_addend, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, long long M, int C, int accumulate_param_grads) {
+                    float* __restrict__ dbeta, long long M, int C, int accumulate_param_grads, const float* __restrict__ mask_beta) {
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
   const float invM = 1.0f / (float)M;
-  float mean[8], istd[8], k1[8], k2[8], gs[8];
+  float mean[8], istd[8], k1[8], k2[8], gs[8], msh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k];
     k1[k] = dsums[c0 + k] * invM; k2[k] = dsums[C + c0 + k] * invM; gs[k] = gamma[c0 + k] * istd[k];
+    msh[k] = mask_beta ? mask_beta[c0 + k] - mean[k] * gs[k] : 0.f;
   }
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
     float g[8], yy[8];
     Vec8<T>::load(dout + i * 8, g);
     Vec8<T>::load(y + i * 8, yy);
-    if (act_out) {
+    if (mask_beta) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = (from_store<T>(fmaxf(yy[k] * gs[k] + msh[k], 0.f)) > 0.f) ? g[k] : 0.f;
+    } else if (act_out) {
       float a[8];
       Vec8<T>::load(act_out + i * 8, a);
 #pragma unroll
@@ -820,22 +831,22 @@ int awr_affine_act(const void* y, const float* scale_shift, const void* res, con
   return AWR_OK;
 }
 
-int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, int dtype, long long M, int C,
-                      float* dsums, void* stream) {
-  AWR_HOST_CHECK(dout && y && mean_invstd && dsums && M > 0 && chan_ok(C));
+int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* mask_gamma,
+                      const float* mask_beta, int dtype, long long M, int C, float* dsums, void* stream) {
+  AWR_HOST_CHECK(dout && y && mean_invstd && dsums && M > 0 && chan_ok(C) && ((mask_gamma == nullptr) == (mask_beta == nullptr)));
   DISPATCH_T(dtype, bn_bwd_reduce_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>(
-                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, dsums));
+                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, dsums, mask_gamma, mask_beta));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
 
 int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* dsums,
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
-                     float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
+                     float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && gamma && dy && M > 0 && chan_ok(C));
   DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>(
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
-                        (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads));
+                        (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads, mask_beta));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

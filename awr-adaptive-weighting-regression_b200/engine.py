@@ -231,6 +231,8 @@ class Plan:
         self.lib = L.lib()
         self.fwd, self.bwd = [], []
         self.fwd_meta, self.bwd_meta = [], []     # per launch: (kernel entry point, algorithmic flops, algorithmic bytes)
+        self.bwd_side = []                        # per backward launch: may run on the side stream (weight gradients: nothing downstream
+                                                  # in the backward pass consumes them, so they overlap the dgrad / BN chain)
         self._arena_total = 0
         self.arena_buf = torch.zeros(1 << 22, dtype=torch.float32, device=device)    # zeroed at the start of every step
         self.ops = []
@@ -257,7 +259,7 @@ class Plan:
             raise RuntimeError("plan arena exhausted")
         return self.arena_buf[off: off + n]
 
-    def call(self, lst, fn, *args, flops=0, nbytes=0, tag=None, detail=""):
+    def call(self, lst, fn, *args, flops=0, nbytes=0, tag=None, detail="", side=False):
         """Bind a C-ABI launch. Tensor-like args are resolved to pointers now (buffers are static).
         flops / nbytes: algorithmic work of this launch (for the roofline report); tag: kernel class label."""
         cargs = [a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args]
@@ -270,6 +272,8 @@ class Plan:
                 L.check(rc, name)
         lst.append(run)
         (self.fwd_meta if lst is self.fwd else self.bwd_meta).append((tag or fn, flops, nbytes, detail))
+        if lst is self.bwd:
+            self.bwd_side.append(bool(side))
 
     def P(self, name):
         return self.store.layout.phys(self.store.params, name)
@@ -288,10 +292,23 @@ class Plan:
         for f in self.fwd:
             f(s)
 
-    def run_backward(self, stream=None):
+    def run_backward(self, stream=None, side=None):
+        """side: optional torch.cuda.Stream.  Launches flagged `side` (weight gradients) are issued there, each after everything
+        enqueued so far on the main stream (its inputs), and the main stream joins the side stream at the end.  Works eagerly and
+        under CUDA-graph capture (the fork/join events become graph edges)."""
         s = L.stream() if stream is None else stream
-        for f in self.bwd:
-            f(s)
+        if side is None:
+            for f in self.bwd:
+                f(s)
+            return
+        main = torch.cuda.current_stream()
+        for f, on_side in zip(self.bwd, self.bwd_side):
+            if on_side:
+                side.wait_stream(main)
+                f(side.cuda_stream)
+            else:
+                f(s)
+        main.wait_stream(side)
 
     # ---- ops ------------------------------------------------------------------------------------------
     def stem(self, wname, bname, Cout, k):
@@ -481,10 +498,10 @@ class _Conv(_Op):
         if pl.tc:
             if not self.transposed:
                 pl.call(pl.bwd, "awr_conv_wgrad_tc", dy, x.t, gW, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k, self.stride,
-                        self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
+                        self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
             else:
                 pl.call(pl.bwd, "awr_conv_wgrad_tc", x.t, dy, gW, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k, self.stride,
-                        self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
+                        self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
             if self.bname:
                 pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
             w16 = pl.W16(self.wname)
@@ -497,10 +514,10 @@ class _Conv(_Op):
         # weight gradient
         if not self.transposed:
             pl.call(pl.bwd, "awr_conv_wgrad_simt", dy, x.t, gW, pl.dt, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k,
-                    self.stride, self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
+                    self.stride, self.pad, self.Cin, 1, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
         else:
             pl.call(pl.bwd, "awr_conv_wgrad_simt", x.t, dy, gW, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
-                    self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail)
+                    self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
         if self.bname:
             pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
         # data gradient
@@ -536,7 +553,8 @@ class _BNAct(_Op):
                     pl.buf(p + ".num_batches_tracked") if tr else None, bn.mi]
         a, b = bnset(self.bn), bnset(self.bn_res)
         rt = res.t if res is not None else (res_y.t if res_y is not None else None)
-        pl.call(pl.fwd, "awr_bn_act", y.t, *a, rt, *b, self.out.t, pl.dt, y.M, y.C, BN_MOMENTUM, BN_EPS, int(tr), int(relu))
+        self.detail = f"bn {y.C}ch @{y.H} N{y.N}{' +res' if res is not None else ''}{' +resbn' if res_y is not None else ''}"
+        pl.call(pl.fwd, "awr_bn_act", y.t, *a, rt, *b, self.out.t, pl.dt, y.M, y.C, BN_MOMENTUM, BN_EPS, int(tr), int(relu), detail=self.detail)
 
     def plan_bwd(self):
         pl, y, out = self.plan, self.y, self.out
@@ -545,7 +563,12 @@ class _BNAct(_Op):
         dout = out.grad()
         act = out.t if self.relu else None
         p = self.prefix
-        pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, y.t, self.bn.mi, pl.dt, y.M, y.C, self.bn.dsums)
+        # ReLU(BN(y)) without a residual: the mask is a function of y, so the backward never reads the activation tensor
+        remask = self.relu and self.res is None and self.res_y is None
+        mg, mb = (pl.P(p + ".weight"), pl.P(p + ".bias")) if remask else (None, None)
+        if remask:
+            act = None
+        pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, y.t, self.bn.mi, mg, mb, pl.dt, y.M, y.C, self.bn.dsums, detail=self.detail)
         dy = y.grad()
         dy_add = dy if y.gw else None
         dres = dres_add = None
@@ -554,14 +577,14 @@ class _BNAct(_Op):
             dres_add = dres if self.res.gw else None
             self.res.gw = True
         pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, y.t, self.bn.mi, self.bn.dsums, pl.P(p + ".weight"), dy, dy_add, dres, dres_add,
-                pl.G(p + ".weight"), pl.G(p + ".bias"), pl.dt, y.M, y.C, 1)
+                pl.G(p + ".weight"), pl.G(p + ".bias"), mb, pl.dt, y.M, y.C, 1, detail=self.detail)
         y.gw = True
         if self.res_y is not None:
             ry, rp = self.res_y, self.res_prefix
-            pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, ry.t, self.bn_res.mi, pl.dt, ry.M, ry.C, self.bn_res.dsums)
+            pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, ry.t, self.bn_res.mi, None, None, pl.dt, ry.M, ry.C, self.bn_res.dsums)
             dry = ry.grad()
             pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, ry.t, self.bn_res.mi, self.bn_res.dsums, pl.P(rp + ".weight"), dry,
-                    dry if ry.gw else None, None, None, pl.G(rp + ".weight"), pl.G(rp + ".bias"), pl.dt, ry.M, ry.C, 1)
+                    dry if ry.gw else None, None, None, pl.G(rp + ".weight"), pl.G(rp + ".bias"), None, pl.dt, ry.M, ry.C, 1)
             ry.gw = True
 
 

@@ -51,6 +51,7 @@ class FusedTrainer:
         self.steps_done = 0
         self.use_graph = use_graph
         self.graph_fb = self.graph_opt = None
+        self.side = torch.cuda.Stream(device=dev)          # weight-gradient GEMMs overlap the dgrad / BatchNorm backward chain
         if self.plan.precision == "bf16":
             self.store.refresh_shadow()
         # launches of OUR kernels per step (memsets / NCCL not counted)
@@ -70,7 +71,7 @@ class FusedTrainer:
         L.check(self.lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), self.uvd.data_ptr(),
                                       self.ws.data_ptr(), None, None, hd.dpred.data_ptr(), self.B, self.J, self.F, self.H, self.ks,
                                       self.cw, self.dw, s), "awr_head_bwd")
-        pl.run_backward(s)
+        pl.run_backward(s, side=self.side)
 
     def _opt(self):
         st, s = self.store, L.stream()

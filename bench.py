@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--net", default="resnet_18")
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU (weak scaling)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--img-size", type=int, default=128, help="depth crop side (128 = headline config; 256 = high-res stress config)")
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg (0 disables)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", default="", help="write a per-layer conv timing table to gpurun_out/<name>")
@@ -189,7 +190,11 @@ def classify_step(tr, steps, layers=None):
 
 
 def main():
+    global H, METRIC
     a = parse()
+    H = a.img_size
+    if a.net != "resnet_18" or H != 128:
+        METRIC = f"training depth-frames/sec (device-timed) {a.net}-AWR {H}x{H}x{J}J"
     if a.impl == "reference":
         return run_reference(a)
 

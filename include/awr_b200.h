@@ -96,14 +96,17 @@ int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* 
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream);
 
-/* BN backward pass 1: dz = dout*(act_out>0) (act_out NULL: no ReLU); dsums[0:C]+=sum dz, dsums[C:2C]+=sum dz*yhat */
-int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, int dtype, long long M, int C,
-                      float* dsums, void* stream);
-/* BN backward pass 2: dy = bn_grad [+ dy_addend]; optional dres = dz [+ dres_addend] (addends may alias their outputs);
+/* BN backward pass 1: dz = dout*mask; dsums[0:C]+=sum dz, dsums[C:2C]+=sum dz*yhat.  ReLU mask: act_out>0 when act_out is given; or, for
+ * ReLU(BN(y)) WITHOUT residual, recomputed from y alone when mask_gamma/mask_beta (the BN affine) are given -- one tensor read less;
+ * all three NULL: no ReLU. */
+int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* mask_gamma,
+                      const float* mask_beta, int dtype, long long M, int C, float* dsums, void* stream);
+/* BN backward pass 2 (mask_beta non-NULL: ReLU mask recomputed from y with gamma/mask_beta instead of reading act_out):
+ * dy = bn_grad [+ dy_addend]; optional dres = dz [+ dres_addend] (addends may alias their outputs);
  * dgamma/dbeta (NULL to skip) written or accumulated. */
 int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* dsums,
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
-                     float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream);
+                     float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream);
 
 /* dx = dout*(act_out>0) [+ addend]   (act_out / addend may be NULL); n elements, n % 8 == 0 */
 int awr_relu_bwd(const void* dout, const void* act_out, const void* addend, void* dx, int dtype, long long n, void* stream);

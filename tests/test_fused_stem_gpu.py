@@ -1,0 +1,68 @@
+"""GPU numerics of the fused stem kernels (through the C-ABI, fp32 storage) vs plain PyTorch fp32:
+stem conv + fused BN statistics, BN+ReLU+MaxPool forward, MaxPool+BN backward (both the 3/2/1 specialisation and the generic path)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def test_stem_conv_with_fused_statistics():
+    from awr_b200 import _lib as L
+    N, H, Co, k = 3, 32, 64, 5
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, 1, H, H, generator=g).cuda()
+    w = (torch.randn(Co, 1, k, k, generator=g) * 0.2).cuda()
+    b = torch.randn(Co, generator=g).cuda()
+    ref = F.conv2d(x, w, b, padding=2)
+    y = torch.empty(N, H, H, Co, device="cuda")
+    stats = torch.zeros(2 * Co, device="cuda")
+    w_phys = w.permute(2, 3, 0, 1).contiguous().view(k * k, Co)
+    L.check(L.lib().awr_stem_conv(x.data_ptr(), w_phys.data_ptr(), b.data_ptr(), y.data_ptr(), stats.data_ptr(), L.F32, N, H, H, Co, k, L.stream()), "stem")
+    torch.cuda.synchronize()
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-5, rtol=1e-5)                    # fp32, tolerance 1e-5
+    assert torch.allclose(stats[:Co], ref.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[Co:], (ref * ref).sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("k,s,p", [(3, 2, 1), (2, 2, 0)])
+def test_bn_relu_maxpool_fwd_and_bwd(k, s, p):
+    from awr_b200 import _lib as L
+    N, C, H = 2, 64, 16
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn(N, C, H, H, generator=g).cuda()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.3).cuda()
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    ref = F.max_pool2d(F.relu(F.batch_norm(yr, rm.clone(), rv.clone(), gr, br, training=True, momentum=0.1, eps=1e-5)), k, s, p)
+    dout = torch.randn(ref.shape, generator=g).cuda()
+    ref.backward(dout)
+    lib = L.lib()
+    yn = _nhwc(y)
+    sums = torch.cat([yn.sum(dim=(0, 1, 2)), (yn * yn).sum(dim=(0, 1, 2))]).contiguous()
+    Ho = ref.shape[-1]
+    out = torch.empty(N, Ho, Ho, C, device="cuda")
+    idx = torch.empty(N, Ho, Ho, C, dtype=torch.uint8, device="cuda")
+    mi = torch.empty(2 * C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    L.check(lib.awr_bn_relu_maxpool_fwd(yn.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(),
+                                        mi.data_ptr(), out.data_ptr(), idx.data_ptr(), L.F32, N, H, H, C, k, s, p, 0.1, 1e-5, 1, L.stream()), "fwd")
+    torch.cuda.synchronize()
+    assert torch.allclose(out.permute(0, 3, 1, 2), ref.detach(), atol=1e-5, rtol=1e-5)
+    assert nbt.item() == 1 and torch.allclose(rm, 0.1 * y.mean(dim=(0, 2, 3)), atol=1e-6)
+    dsums = torch.zeros(2 * C, device="cuda")
+    dy = torch.empty_like(yn)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dpool = _nhwc(dout)
+    for ps in (0, 1):
+        L.check(lib.awr_maxpool_bn_bwd(dpool.data_ptr(), idx.data_ptr(), yn.data_ptr(), mi.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dsums.data_ptr(),
+                                       dy.data_ptr(), dg.data_ptr(), db.data_ptr(), L.F32, N, H, H, C, k, s, p, ps, 0, L.stream()), "bwd")
+    torch.cuda.synchronize()
+    scale = yr.grad.abs().max().item()
+    assert (dy.permute(0, 3, 1, 2) - yr.grad).abs().max().item() < 1e-4 * scale + 1e-6
+    assert torch.allclose(dg, gr.grad, rtol=1e-4, atol=1e-4) and torch.allclose(db, br.grad, rtol=1e-4, atol=1e-4)

@@ -14,6 +14,28 @@
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be scheduled while
+// the previous kernel of the stream is still draining, run their prologue (smem carve-up, mbarrier init, TMEM alloc, tensor-map
+// prefetch) and then block in pdl_wait() until the previous grid has completed and flushed.  No global memory is touched before
+// pdl_wait().  pdl_trigger() at kernel entry lets the NEXT kernel do the same with respect to this one.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

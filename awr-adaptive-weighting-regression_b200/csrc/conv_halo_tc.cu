@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
                  void* __restrict__ outp, float* __restrict__ stats, const __grid_constant__ HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();                 // the next kernel may start its prologue while this grid runs
   __shared__ __align__(8) uint64_t hfull[kHaloStages], hempty[kHaloStages], bfull[8], bempty[8], tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -92,6 +93,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();                    // prologue done; from here on the previous kernel's outputs are visible
 
   if (warp == 4) {
     // ======================================= TMA producer =======================================
@@ -383,7 +385,7 @@ int conv_halo_launch(const ConvGeom& g, const void* in, const void* w, const flo
   }
   const int total = p.nclasses * p.tiles_c * p.items_m;
   const int grid = total < 148 ? total : 148;
-  conv_halo_kernel<<<grid, kThreads, smem, stream>>>(maps, tmB, bias, out, stats, p);
+  if (launch_pdl(conv_halo_kernel, dim3(grid), dim3(kThreads), smem, stream, maps, tmB, bias, out, stats, p) != cudaSuccess) return (int)cudaGetLastError();
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -39,6 +39,7 @@ struct GatherP {
 template <typename T>
 __global__ void __launch_bounds__(256) conv_gather_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                           const float* __restrict__ bias, void* __restrict__ outp, GatherP p) {
+  pdl_entry();
   __shared__ __align__(16) float As[TK][LD];
   __shared__ __align__(16) float Bs[TK][LD];
   const int tid = threadIdx.x;
@@ -140,6 +141,7 @@ struct WgradP {
 // dW[tap][i*s_p + j*s_g] += sum_{coarse pixel q} P[q, i] * G[q*stride - pad + tap, j]
 template <typename T>
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const T* __restrict__ Pt, const T* __restrict__ Gt, float* __restrict__ dW, WgradP p) {
+  pdl_entry();
   __shared__ __align__(16) float Ps[TK][LD];
   __shared__ __align__(16) float Gs[TK][LD];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const T* __restrict__ P
 template <typename T>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                         T* __restrict__ y, int N, int H, int W, int Cout, int k) {
+  pdl_entry();
   extern __shared__ float ws[];   // [k*k][Cout]
   for (int i = threadIdx.x; i < k * k * Cout; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
                                                          float* __restrict__ dbias, int N, int H, int W, int Cout, int k, int pix_per_block) {
+  pdl_entry();
   const int co = threadIdx.x % Cout, tg = threadIdx.x / Cout, ngroups = blockDim.x / Cout;
   const int pad = k / 2, taps = k * k;
   const long long P = (long long)N * H * W;
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 template <typename T, int K>
 __global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
                                                                float* __restrict__ dbias, int N, int H, int W) {
+  pdl_entry();
   constexpr int RB = 8, CO = 64, PADK = K / 2, XS = 8 + K - 1;
   extern __shared__ __align__(16) float sm[];
   const int pitch = ((W + K - 1) + 3) & ~3;
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __re
 template <typename T, int K>
 __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                               T* __restrict__ y, float* __restrict__ stats, int N, int H, int W, int Cout) {
+  pdl_entry();
   extern __shared__ __align__(16) float ws[];   // [K*K][Cout] then reduction scratch
   for (int i = threadIdx.x; i < K * K * Cout; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -403,7 +409,7 @@ int awr_conv_simt(const void* in, const float* w, const float* bias, void* out, 
   GatherP p{N, Hi, Wi, Ck, Ho, Wo, Cn, R, S, stride, pad, transposed, w_sk, w_sn, w_tap, out_mode, n_valid, accumulate};
   const long long M = (long long)N * Ho * Wo;
   dim3 grid((unsigned)((M + TM - 1) / TM), Cn / TN);
-  DISPATCH_T(dtype, conv_gather_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)in, w, bias, out, p));
+  DISPATCH_T(dtype, launch_pdl(conv_gather_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)in, w, bias, out, p));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -419,7 +425,7 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, 
   if (ksplit < 1) ksplit = 1;
   WgradP p{N, Hc, Wc, Cp, Hf, Wf, Cg, R, S, stride, pad, s_p, s_g, w_tap, ksplit};
   dim3 grid((Cp / TM) * (Cg / TN), R * S, ksplit);
-  DISPATCH_T(dtype, conv_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)pointwise, (const T*)gathered, dW, p));
+  DISPATCH_T(dtype, launch_pdl(conv_wgrad_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)pointwise, (const T*)gathered, dW, p));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -433,7 +439,7 @@ int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, fl
     if (blocks4 > 148 * 8) blocks4 = 148 * 8;
     size_t smem4 = (size_t)k * k * Cout * sizeof(float);
     if (smem4 < 256 * 16 * sizeof(float)) smem4 = 256 * 16 * sizeof(float);
-    DISPATCH_T(dtype, stem_conv_tiled_kernel<T, 5><<<(int)blocks4, 256, smem4, (cudaStream_t)stream>>>(x, w, bias, (T*)y, stats, N, H, W, Cout));
+    DISPATCH_T(dtype, launch_pdl(stem_conv_tiled_kernel<T, 5>, dim3((int)blocks4), dim3(256), smem4, (cudaStream_t)stream, x, w, bias, (T*)y, stats, N, H, W, Cout));
     AWR_LAUNCH_CHECK();
     return AWR_OK;
   }
@@ -442,7 +448,7 @@ int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, fl
   long long blocks = (items + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   const size_t smem = (size_t)k * k * Cout * sizeof(float);
-  DISPATCH_T(dtype, stem_conv_kernel<T><<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (T*)y, N, H, W, Cout, k));
+  DISPATCH_T(dtype, launch_pdl(stem_conv_kernel<T>, dim3((int)blocks), dim3(256), smem, (cudaStream_t)stream, x, w, bias, (T*)y, N, H, W, Cout, k));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -458,11 +464,11 @@ int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int 
   if (k == 5 && Cout == 64 && H % 8 == 0 && W % 8 == 0 && W <= 256) {
     const int pitch = ((W + 4) + 3) & ~3;
     const size_t smem = ((size_t)12 * pitch + 4 * 26 * 64) * sizeof(float);
-    DISPATCH_T(dtype, stem_wgrad_tiled_kernel<T, 5><<<N * (H / 8), 256, smem, (cudaStream_t)stream>>>(x, (const T*)dy, dW, dbias, N, H, W));
+    DISPATCH_T(dtype, launch_pdl(stem_wgrad_tiled_kernel<T, 5>, dim3(N * (H / 8)), dim3(256), smem, (cudaStream_t)stream, x, (const T*)dy, dW, dbias, N, H, W));
     AWR_LAUNCH_CHECK();
     return AWR_OK;
   }
-  DISPATCH_T(dtype, stem_wgrad_kernel<T><<<(int)((P + ppb - 1) / ppb), 256, 0, (cudaStream_t)stream>>>(x, (const T*)dy, dW, dbias, N, H,
+  DISPATCH_T(dtype, launch_pdl(stem_wgrad_kernel<T>, dim3((int)((P + ppb - 1) / ppb)), dim3(256), 0, (cudaStream_t)stream, x, (const T*)dy, dW, dbias, N, H,
                                                                                                       W, Cout, k, ppb));
   AWR_LAUNCH_CHECK();
   return AWR_OK;

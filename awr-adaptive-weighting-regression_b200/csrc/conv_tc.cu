@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
                void* __restrict__ outp, float* __restrict__ stats, const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();                 // the next kernel may start its prologue while this grid runs
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -87,6 +88,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();                    // prologue done; from here on the previous kernel's outputs are visible
 
   if (warp == 4) {
     // ======================================= TMA producer =======================================
@@ -393,7 +395,7 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
   const int total_tiles = p.nclasses * p.tiles_m * p.tiles_c;
   int sms = 148;
   int grid = total_tiles < sms ? total_tiles : sms;
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA, tmB, bias, out, stats, p);
+  if (launch_pdl(conv_tc_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, tmA, tmB, bias, out, stats, p) != cudaSuccess) return (int)cudaGetLastError();
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

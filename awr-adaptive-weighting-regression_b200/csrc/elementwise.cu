@@ -55,6 +55,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int G,
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads) channel_stats_kernel(const T* __restrict__ x, long long M, int C, float* __restrict__ sums, int with_sq) {
+  pdl_entry();
   __shared__ float smem[kEwThreads * 8];
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
@@ -81,6 +82,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, 
                                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale_shift,
                                    float* __restrict__ mean_invstd, int C, float momentum, float eps, int training) {
+  pdl_entry();
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     float mean, invstd;
     if (training) {
@@ -112,6 +114,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 affine_act_kernel(const T* __restrict__ y, const float* __restrict__ ss, const T* __restrict__ res, const float* __restrict__ res_ss,
                   T* __restrict__ out, long long M, int C, int relu) {
+  pdl_entry();
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
@@ -181,6 +184,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSet rbn, int res_has_bn, T* __restrict__ out, long long M, int C,
               float count, float momentum, float eps, int training, int relu) {
+  pdl_entry();
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
@@ -229,6 +233,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 bn_relu_maxpool_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ out, unsigned char* __restrict__ idx, int N, int H, int W, int C,
                            int Ho, int Wo, int k, int s, int p, float count, float momentum, float eps, int training) {
+  pdl_entry();
   const int G = C >> 3;
   const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
@@ -278,6 +283,7 @@ maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restri
                       const float* __restrict__ mean_invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                       float* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
                       int C, int Ho, int Wo, int k, int s, int p, int pass, int accumulate_param_grads) {
+  pdl_entry();
   __shared__ float smem[kEwThreads * 8];
   const int G = C >> 3;
   const long long items = (long long)N * H * W * G, stride = (long long)gridDim.x * kEwThreads;
@@ -342,6 +348,7 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
                          const float* __restrict__ mean_invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
                          int C, int pass, int accumulate_param_grads) {
+  pdl_entry();
   __shared__ float smem[kEwThreads * 8];
   const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
@@ -423,6 +430,7 @@ __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
                      const float* __restrict__ mean_invstd, long long M, int C, float* __restrict__ dsums,
                      const float* __restrict__ mask_gamma, const float* __restrict__ mask_beta) {
+  pdl_entry();
   __shared__ float smem[kEwThreads * 8];
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
@@ -461,6 +469,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
                     const float* __restrict__ mean_invstd, const float* __restrict__ dsums, const float* __restrict__ gamma,
                     T* dy, const T* dy_addend, T* dres, const T* dres_addend, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, long long M, int C, int accumulate_param_grads, const float* __restrict__ mask_beta) {
+  pdl_entry();
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
@@ -517,6 +526,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 relu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ addend, T* __restrict__ dx, long long n8) {
+  pdl_entry();
   const long long stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n8; i += stride) {
     float g[8];
@@ -544,6 +554,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, unsigned char* __restrict__ idx, int N, int H, int W, int C, int Ho,
                    int Wo, int k, int s, int p) {
+  pdl_entry();
   const int G = C >> 3;
   const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
@@ -584,6 +595,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 maxpool_bwd_kernel(const T* __restrict__ dout, const unsigned char* __restrict__ idx, T* __restrict__ dx, int N, int H, int W, int C,
                    int Ho, int Wo, int k, int s, int p, int accumulate) {
+  pdl_entry();
   const int G = C >> 3;
   const long long items = (long long)N * H * W * G, stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
@@ -623,6 +635,7 @@ maxpool_bwd_kernel(const T* __restrict__ dout, const unsigned char* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 upsample2_add_kernel(const T* __restrict__ up, const T* __restrict__ low, T* __restrict__ out, int N, int H, int W, int C) {
+  pdl_entry();
   const int G = C >> 3;
   const long long items = (long long)N * H * W * G, stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
@@ -642,7 +655,8 @@ upsample2_add_kernel(const T* __restrict__ up, const T* __restrict__ low, T* __r
 // backward of the up-sample branch: dlow[n,h2,w2,c] = sum of the 2x2 block of dout
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
-upsample2_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dlow, int N, int H, int W, int C, int accumulate) {   // H,W = fine size
+upsample2_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dlow, int N, int H, int W, int C, int accumulate) {
+  pdl_entry();   // H,W = fine size
   const int G = C >> 3, H2 = H / 2, W2 = W / 2;
   const long long items = (long long)N * H2 * W2 * G, stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
@@ -671,6 +685,7 @@ upsample2_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dlow, int N, in
 // src NCHW fp32 (N,Csrc,P) -> dst NHWC T (N,P,Cdst), channels >= Csrc zero-filled. 32x32 smem transpose tiles.
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int Csrc, int Cdst, int P) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -686,6 +701,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 // src NHWC T (N,P,Csrc) -> dst NCHW fp32 (N,Cdst,P) taking the first Cdst channels
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int Csrc, int Cdst, int P) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -705,6 +721,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
 __global__ void __launch_bounds__(kEwThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow,
             long long n, const float* __restrict__ step_dev, float lr, float b1, float b2, float eps, float wd, float grad_scale) {
+  pdl_entry();
   // step_dev[0] holds the 1-based step count as float (updated by the caller's graph via awr_adam_tick)
   const float step = __ldg(step_dev);
   const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
@@ -739,9 +756,11 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
   }
 }
-__global__ void adam_tick_kernel(float* step_dev) { step_dev[0] += 1.f; }
+__global__ void adam_tick_kernel(float* step_dev) {
+  pdl_entry(); step_dev[0] += 1.f; }
 
 __global__ void __launch_bounds__(kEwThreads) cast_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  pdl_entry();
   const long long stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
 }
@@ -757,7 +776,7 @@ extern "C" {
 
 int awr_channel_stats(const void* x, int dtype, long long M, int C, float* sums, int with_sq, void* stream) {
   AWR_HOST_CHECK(x && sums && M > 0 && chan_ok(C));
-  DISPATCH_T(dtype, channel_stats_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)x, M, C, sums, with_sq));
+  DISPATCH_T(dtype, launch_pdl(channel_stats_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)x, M, C, sums, with_sq));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -766,7 +785,7 @@ int awr_bn_finalize(const float* sums, long long count, const float* gamma, cons
                     float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_invstd, int C,
                     float momentum, float eps, int training, void* stream) {
   AWR_HOST_CHECK(gamma && beta && scale_shift && C > 0 && (training ? (sums != nullptr && count > 0) : (running_mean && running_var)));
-  bn_finalize_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, (float)count, gamma, beta, running_mean, running_var,
+  launch_pdl(bn_finalize_kernel, dim3((C + 255) / 256), dim3(256), 0, (cudaStream_t)stream, sums, (float)count, gamma, beta, running_mean, running_var,
                                                                        num_batches_tracked, scale_shift, mean_invstd, C, momentum,
                                                                        eps, training);
   AWR_LAUNCH_CHECK();
@@ -784,7 +803,7 @@ int awr_bn_act(const void* y, const float* sums, const float* gamma, const float
   AWR_HOST_CHECK(!res_has_bn || (res && res_beta && (training ? (res_sums != nullptr) : (res_running_mean && res_running_var))));
   BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
   BnSet b{res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
-  DISPATCH_T(dtype, bn_act_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)y, a, (const T*)res, b, res_has_bn, (T*)out, M,
+  DISPATCH_T(dtype, launch_pdl(bn_act_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a, (const T*)res, b, res_has_bn, (T*)out, M,
                                                                                              C, (float)M, momentum, eps, training, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -797,7 +816,7 @@ int awr_bn_relu_maxpool_fwd(const void* y, const float* sums, const float* gamma
   AWR_HOST_CHECK(training ? (sums != nullptr) : (running_mean && running_var));
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
   BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
-  DISPATCH_T(dtype, bn_relu_maxpool_fwd_kernel<T><<<red_blocks((long long)N * Ho * Wo, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(bn_relu_maxpool_fwd_kernel<T>, dim3(red_blocks((long long)N * Ho * Wo, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)y, a, (T*)out, idx, N, H, W, C, Ho, Wo, k, s, p, (float)((long long)N * H * W), momentum, eps, training));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -809,13 +828,13 @@ int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* 
   AWR_HOST_CHECK(dpool && idx && y && mean_invstd && gamma && beta && dsums && N > 0 && chan_ok(C) && (pass == 0 || dy != nullptr));
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
   if (k == 3 && s == 2 && p == 1 && H % 2 == 0 && W % 2 == 0) {
-    DISPATCH_T(dtype, maxpool3s2_bn_bwd_kernel<T><<<red_blocks((long long)N * Ho * Wo * 2, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+    DISPATCH_T(dtype, launch_pdl(maxpool3s2_bn_bwd_kernel<T>, dim3(red_blocks((long long)N * Ho * Wo * 2, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                           (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, dsums, (T*)dy, dgamma, dbeta, N, H, W, C, pass,
                           accumulate_param_grads));
     AWR_LAUNCH_CHECK();
     return AWR_OK;
   }
-  DISPATCH_T(dtype, maxpool_bn_bwd_kernel<T><<<red_blocks((long long)N * H * W, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(maxpool_bn_bwd_kernel<T>, dim3(red_blocks((long long)N * H * W, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, dsums, (T*)dy, dgamma, dbeta, N, H, W, C, Ho, Wo, k, s, p,
                         pass, accumulate_param_grads));
   AWR_LAUNCH_CHECK();
@@ -825,7 +844,7 @@ int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* 
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream) {
   AWR_HOST_CHECK(y && out && M > 0 && C % 8 == 0);
-  DISPATCH_T(dtype, affine_act_kernel<T><<<ew_blocks(M * (C / 8)), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(affine_act_kernel<T>, dim3(ew_blocks(M * (C / 8))), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M, C, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -834,7 +853,7 @@ int awr_affine_act(const void* y, const float* scale_shift, const void* res, con
 int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* mask_gamma,
                       const float* mask_beta, int dtype, long long M, int C, float* dsums, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && M > 0 && chan_ok(C) && ((mask_gamma == nullptr) == (mask_beta == nullptr)));
-  DISPATCH_T(dtype, bn_bwd_reduce_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(bn_bwd_reduce_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, dsums, mask_gamma, mask_beta));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -844,7 +863,7 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && gamma && dy && M > 0 && chan_ok(C));
-  DISPATCH_T(dtype, bn_bwd_apply_kernel<T><<<red_blocks(M, C), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(bn_bwd_apply_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
                         (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads, mask_beta));
   AWR_LAUNCH_CHECK();
@@ -853,7 +872,7 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
 
 int awr_relu_bwd(const void* dout, const void* act_out, const void* addend, void* dx, int dtype, long long n, void* stream) {
   AWR_HOST_CHECK(dout && dx && n > 0 && n % 8 == 0);
-  DISPATCH_T(dtype, relu_bwd_kernel<T><<<ew_blocks(n / 8), kEwThreads, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)act_out,
+  DISPATCH_T(dtype, launch_pdl(relu_bwd_kernel<T>, dim3(ew_blocks(n / 8)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)dout, (const T*)act_out,
                                                                                                  (const T*)addend, (T*)dx, n / 8));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -863,7 +882,7 @@ int awr_maxpool_fwd(const void* x, void* out, unsigned char* idx, int dtype, int
                     void* stream) {
   AWR_HOST_CHECK(x && out && N > 0 && C % 8 == 0 && k >= 1 && k <= 3 && s >= 1);
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
-  DISPATCH_T(dtype, maxpool_fwd_kernel<T><<<ew_blocks((long long)N * Ho * Wo * (C / 8), 2), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(maxpool_fwd_kernel<T>, dim3(ew_blocks((long long)N * Ho * Wo * (C / 8), 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)x, (T*)out, idx, N, H, W, C, Ho, Wo, k, s, p));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -873,7 +892,7 @@ int awr_maxpool_bwd(const void* dout, const unsigned char* idx, void* dx, int dt
                     int accumulate, void* stream) {
   AWR_HOST_CHECK(dout && idx && dx && N > 0 && C % 8 == 0);
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
-  DISPATCH_T(dtype, maxpool_bwd_kernel<T><<<ew_blocks((long long)N * H * W * (C / 8), 2), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(maxpool_bwd_kernel<T>, dim3(ew_blocks((long long)N * H * W * (C / 8), 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)dout, idx, (T*)dx, N, H, W, C, Ho, Wo, k, s, p, accumulate));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -881,7 +900,7 @@ int awr_maxpool_bwd(const void* dout, const unsigned char* idx, void* dx, int dt
 
 int awr_upsample2_add(const void* up, const void* low, void* out, int dtype, int N, int H, int W, int C, void* stream) {
   AWR_HOST_CHECK(up && low && out && N > 0 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0);
-  DISPATCH_T(dtype, upsample2_add_kernel<T><<<ew_blocks((long long)N * H * W * (C / 8)), kEwThreads, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, launch_pdl(upsample2_add_kernel<T>, dim3(ew_blocks((long long)N * H * W * (C / 8))), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)up, (const T*)low, (T*)out, N, H, W, C));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -889,8 +908,7 @@ int awr_upsample2_add(const void* up, const void* low, void* out, int dtype, int
 
 int awr_upsample2_bwd(const void* dout, void* dlow, int dtype, int N, int H, int W, int C, int accumulate, void* stream) {
   AWR_HOST_CHECK(dout && dlow && N > 0 && C % 8 == 0 && H % 2 == 0 && W % 2 == 0);
-  DISPATCH_T(dtype, upsample2_bwd_kernel<T><<<ew_blocks((long long)N * (H / 2) * (W / 2) * (C / 8), 2), kEwThreads, 0,
-                                              (cudaStream_t)stream>>>((const T*)dout, (T*)dlow, N, H, W, C, accumulate));
+  DISPATCH_T(dtype, launch_pdl(upsample2_bwd_kernel<T>, dim3(ew_blocks((long long)N * (H / 2) * (W / 2) * (C / 8), 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)dout, (T*)dlow, N, H, W, C, accumulate));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -898,7 +916,7 @@ int awr_upsample2_bwd(const void* dout, void* dlow, int dtype, int N, int H, int
 int awr_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int Csrc, int Cdst, int P, void* stream) {
   AWR_HOST_CHECK(src && dst && N > 0 && Csrc > 0 && Cdst >= Csrc && P > 0);
   dim3 grid((P + 31) / 32, (Cdst + 31) / 32, N), block(32, 8);
-  DISPATCH_T(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(src, (T*)dst, Csrc, Cdst, P));
+  DISPATCH_T(dtype, launch_pdl(nchw_to_nhwc_kernel<T>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (T*)dst, Csrc, Cdst, P));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -906,7 +924,7 @@ int awr_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int Csrc, in
 int awr_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, int Csrc, int Cdst, int P, void* stream) {
   AWR_HOST_CHECK(src && dst && N > 0 && Cdst > 0 && Cdst <= Csrc && P > 0);
   dim3 grid((P + 31) / 32, (Cdst + 31) / 32, N), block(32, 8);
-  DISPATCH_T(dtype, nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)src, dst, Csrc, Cdst, P));
+  DISPATCH_T(dtype, launch_pdl(nhwc_to_nchw_kernel<T>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, (const T*)src, dst, Csrc, Cdst, P));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -914,7 +932,7 @@ int awr_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, int Csrc, in
 int awr_adam_flat(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* step_dev, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream) {
   AWR_HOST_CHECK(p && g && m && v && step_dev && n > 0);
-  adam_kernel<<<ew_blocks((n + 3) / 4, 2), kEwThreads, 0, (cudaStream_t)stream>>>(p, g, m, v, (bf16*)bf16_shadow, n, step_dev, lr, beta1,
+  launch_pdl(adam_kernel, dim3(ew_blocks((n + 3) / 4, 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, p, g, m, v, (bf16*)bf16_shadow, n, step_dev, lr, beta1,
                                                                                 beta2, eps, weight_decay, grad_scale);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -922,14 +940,14 @@ int awr_adam_flat(float* p, const float* g, float* m, float* v, void* bf16_shado
 
 int awr_adam_tick(float* step_dev, void* stream) {
   AWR_HOST_CHECK(step_dev);
-  adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  launch_pdl(adam_tick_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
 
 int awr_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   AWR_HOST_CHECK(src && dst && n > 0);
-  cast_f32_to_bf16_kernel<<<ew_blocks(n), kEwThreads, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  launch_pdl(cast_f32_to_bf16_kernel, dim3(ew_blocks(n)), dim3(kEwThreads), 0, (cudaStream_t)stream, src, (bf16*)dst, n);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kHeadThreads, 4)
 head_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const float* __restrict__ jt_gt,
                 float* __restrict__ uvd_out, float* __restrict__ stats, float* __restrict__ partial,
                 unsigned* __restrict__ counter, float* __restrict__ loss_out, int B, int J, int F, int H, float ks) {
+  pdl_entry();
   __shared__ float red[6 * 32];
   __shared__ __align__(16) float ax[256];
   fill_axis(ax, F);
@@ -201,6 +202,7 @@ head_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
                 const float* __restrict__ uvd, const float* __restrict__ stats, const float* __restrict__ g_uvd,
                 const float* __restrict__ loss_grad, float* __restrict__ dpred, int B, int J, int F, int H, float ks,
                 float cw, float dw) {
+  pdl_entry();
   __shared__ __align__(16) float ax[256];
   fill_axis(ax, F);
   const int bj = blockIdx.x, b = bj / J, j = bj - b * J;
@@ -276,6 +278,7 @@ head_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
 __global__ void __launch_bounds__(kHeadThreads)
 joint2offset_kernel(const float* __restrict__ jt, const float* __restrict__ img, float* __restrict__ out, int B, int J,
                     int F, int H, float ks) {
+  pdl_entry();
   const int bj = blockIdx.x, b = bj / J, j = bj - b * J;
   const int P = F * F, step = H / F;
   const float Ff = (float)F;
@@ -304,6 +307,7 @@ joint2offset_kernel(const float* __restrict__ jt, const float* __restrict__ img,
 __global__ void __launch_bounds__(256)
 huber_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float* __restrict__ partial,
                  unsigned* __restrict__ counter, float* __restrict__ out) {
+  pdl_entry();
   __shared__ float red[2 * 32];
   float acc[2] = {0.f, 0.f};
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -316,6 +320,7 @@ huber_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long 
 __global__ void __launch_bounds__(256)
 huber_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, const float* __restrict__ gout,
                  float* __restrict__ dx) {
+  pdl_entry();
   const float k = (gout ? __ldg(gout) : 1.0f) / (float)n;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dx[i] = k * huber_grad(x[i] - y[i]);
@@ -336,10 +341,10 @@ int awr_head_fwd(const void* pred, int pred_dtype, const float* img, const float
   float* partial = ws + 2 * (size_t)B * J;
   unsigned* counter = reinterpret_cast<unsigned*>(ws + 4 * (size_t)B * J);
   if (pred_dtype == AWR_DTYPE_F32)
-    head_fwd_kernel<float><<<B * J, kHeadThreads, 0, st>>>((const float*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
+    launch_pdl(head_fwd_kernel<float>, dim3(B * J), dim3(kHeadThreads), 0, st, (const float*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
                                                            loss_out, B, J, F, H, kernel_size);
   else if (pred_dtype == AWR_DTYPE_BF16)
-    head_fwd_kernel<bf16><<<B * J, kHeadThreads, 0, st>>>((const bf16*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
+    launch_pdl(head_fwd_kernel<bf16>, dim3(B * J), dim3(kHeadThreads), 0, st, (const bf16*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
                                                           loss_out, B, J, F, H, kernel_size);
   else
     return AWR_ERR_UNSUPPORTED;
@@ -354,10 +359,10 @@ int awr_head_bwd(const void* pred, int pred_dtype, const float* img, const float
   AWR_HOST_CHECK(uvd_gt != nullptr || g_uvd != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
   if (pred_dtype == AWR_DTYPE_F32)
-    head_bwd_kernel<float><<<B * J, kHeadThreads, 0, st>>>((const float*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B,
+    launch_pdl(head_bwd_kernel<float>, dim3(B * J), dim3(kHeadThreads), 0, st, (const float*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B,
                                                            J, F, H, kernel_size, coord_weight, dense_weight);
   else if (pred_dtype == AWR_DTYPE_BF16)
-    head_bwd_kernel<bf16><<<B * J, kHeadThreads, 0, st>>>((const bf16*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B, J,
+    launch_pdl(head_bwd_kernel<bf16>, dim3(B * J), dim3(kHeadThreads), 0, st, (const bf16*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B, J,
                                                           F, H, kernel_size, coord_weight, dense_weight);
   else
     return AWR_ERR_UNSUPPORTED;
@@ -368,7 +373,7 @@ int awr_head_bwd(const void* pred, int pred_dtype, const float* img, const float
 int awr_joint2offset(const float* jt_uvd, const float* img, float* out, int B, int J, int F, int H, float kernel_size,
                      void* stream) {
   AWR_HOST_CHECK(jt_uvd && img && out && head_args_ok(B, J, F, H));
-  joint2offset_kernel<<<B * J, kHeadThreads, 0, (cudaStream_t)stream>>>(jt_uvd, img, out, B, J, F, H, kernel_size);
+  launch_pdl(joint2offset_kernel, dim3(B * J), dim3(kHeadThreads), 0, (cudaStream_t)stream, jt_uvd, img, out, B, J, F, H, kernel_size);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -378,7 +383,7 @@ int awr_huber_fwd(const float* x, const float* y, long long n, float* ws, float*
   int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
   if (blocks > AWR_HUBER_MAX_BLOCKS) blocks = AWR_HUBER_MAX_BLOCKS;
   unsigned* counter = reinterpret_cast<unsigned*>(ws + 2 * AWR_HUBER_MAX_BLOCKS);
-  huber_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, ws, counter, out);
+  launch_pdl(huber_fwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, y, n, ws, counter, out);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -387,7 +392,7 @@ int awr_huber_bwd(const float* x, const float* y, long long n, const float* grad
   AWR_HOST_CHECK(x && y && dx && n > 0);
   int blocks = (int)((n + 256 * 8 - 1) / (256 * 8));
   if (blocks > 148 * 16) blocks = 148 * 16;
-  huber_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n, grad_out, dx);
+  launch_pdl(huber_bwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, x, y, n, grad_out, dx);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

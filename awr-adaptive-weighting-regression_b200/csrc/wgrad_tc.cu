@@ -54,6 +54,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmG3, const __grid_constant__ CUtensorMap tmP, float* __restrict__ dW,
                 const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();                 // the next kernel may start its prologue while this grid runs
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar;
   __shared__ uint32_t tmem_base_s;
 
@@ -88,6 +89,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();                    // prologue done; from here on the previous kernel's outputs are visible
 
   if (warp == 4) {
     // ======================================= TMA producer =======================================
@@ -317,7 +319,7 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  wgrad_tc_kernel<<<base_items * ksplit, kThreads, smem, (cudaStream_t)stream>>>(tmG[0], tmG[1], tmG[2], tmG[3], tmP, dW, p);
+  if (launch_pdl(wgrad_tc_kernel, dim3(base_items * ksplit), dim3(kThreads), smem, (cudaStream_t)stream, tmG[0], tmG[1], tmG[2], tmG[3], tmP, dW, p) != cudaSuccess) return (int)cudaGetLastError();
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -149,28 +149,40 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
         { HPROF_T0(); mbar_wait(&hfull[hs], hph); if (lane == 0) HPROF_ADD(2); }
         tc_fence_after();
         const uint64_t ah = adesc0 + (uint64_t)((uint32_t)(hs * kHaloStageBytes) >> 4);
-        for (int t = 0; t < ntaps; ++t) {
-          { HPROF_T0(); mbar_wait(&bfull[bs], bph); if (lane == 0) HPROF_ADD(3); }
+        // taps are issued in pairs (16 MMAs per elected-lane block): the ~130-cycle issue bubble per block (probe:
+        // tools/dbg_umma_pipe.py) is then paid once per two weight tiles
+        for (int t = 0; t < ntaps; t += 2) {
+          const bool two = (t + 1 < ntaps);
+          int bs2 = bs + 1; uint32_t bph2 = bph;
+          if (bs2 == p.b_stages) { bs2 = 0; bph2 ^= 1u; }
+          { HPROF_T0(); mbar_wait(&bfull[bs], bph); if (two) mbar_wait(&bfull[bs2], bph2); if (lane == 0) HPROF_ADD(3); }
           tc_fence_after();
           if (elect_one()) {
             HPROF_T0();
-            const uint64_t a0 = ah + (uint64_t)(uint32_t)hc.aoff[t];
-            const uint64_t a1 = a0 + 64;                       // sub-tile 1 = 8 pixels (1024 B) to the right
-            const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * bsstep);
-            umma_bf16(d0, a0, bd, idesc, first ? 0u : 1u);
-            umma_bf16(d1, a1, bd, idesc, first ? 0u : 1u);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
-              umma_bf16(d0, a0 + 2 * k, bd + k * bstep, idesc, 1u);
-              umma_bf16(d1, a1 + 2 * k, bd + k * bstep, idesc, 1u);
+            for (int u = 0; u < 2; ++u) {
+              if (u == 1 && !two) break;
+              const int tt = t + u, sb_ = u ? bs2 : bs;
+              const uint64_t a0 = ah + (uint64_t)(uint32_t)hc.aoff[tt];
+              const uint64_t a1 = a0 + 64;                       // sub-tile 1 = 8 pixels (1024 B) to the right
+              const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)sb_ * bsstep);
+              umma_bf16(d0, a0, bd, idesc, first ? 0u : 1u);
+              umma_bf16(d1, a1, bd, idesc, first ? 0u : 1u);
+              first = 0;
+#pragma unroll
+              for (int k = 1; k < 4; ++k) {
+                umma_bf16(d0, a0 + 2 * k, bd + k * bstep, idesc, 1u);
+                umma_bf16(d1, a1 + 2 * k, bd + k * bstep, idesc, 1u);
+              }
+              umma_commit(&bempty[sb_]);
+              if (tt == ntaps - 1) umma_commit(&hempty[hs]);
             }
-            umma_commit(&bempty[bs]);
-            if (t == ntaps - 1) umma_commit(&hempty[hs]);
             HPROF_ADD(9);
           }
           __syncwarp();
           first = 0;
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1u; }
+          bs = bs2; bph = bph2;
+          if (two) { if (++bs == p.b_stages) { bs = 0; bph ^= 1u; } }
         }
         if (++hs == kHaloStages) { hs = 0; hph ^= 1u; }
       }
@@ -258,11 +270,19 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
           const int pairs = p.Ntile >> 1, slices = 128 / pairs, rows_per = 128 / slices;
           const int cp = et % pairs, sl = et / pairs;
           float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-          for (int rr = sl * rows_per; rr < (sl + 1) * rows_per; ++rr) {
-            const int lc = cp >> 2, pc = lc ^ (rr & (chunks16 - 1));
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + rr * row_bytes + pc * 16 + (cp & 3) * 4);
-            const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-            s1a += x.x; s1b += x.y; s2a += x.x * x.x; s2b += x.y * x.y;
+          const int lcs = cp >> 2, wofs = (cp & 3) * 4;
+          for (int rr = sl * rows_per; rr < (sl + 1) * rows_per; rr += 8) {      // rows_per is a multiple of 8: 8 independent loads in flight
+            uint32_t u[8];
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const int r8 = rr + k8;
+              u[k8] = *reinterpret_cast<const uint32_t*>(stg + r8 * row_bytes + ((lcs ^ (r8 & (chunks16 - 1))) << 4) + wofs);
+            }
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[k8]));
+              s1a += x.x; s1b += x.y; s2a += x.x * x.x; s2b += x.y * x.y;
+            }
           }
           atomicAdd(s_stats + c0 + 2 * cp, s1a); atomicAdd(s_stats + c0 + 2 * cp + 1, s1b);
           atomicAdd(s_stats + p.Cn + c0 + 2 * cp, s2a); atomicAdd(s_stats + p.Cn + c0 + 2 * cp + 1, s2b);
@@ -272,14 +292,28 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
           const int tpp = chunks16, ppp = 128 / tpp;                          // threads per pixel, pixels per pass
           const int lc = et % tpp, pr = et / tpp;
           bf16* const outb = reinterpret_cast<bf16*>(outp);
-          for (int pass = 0; pass < 128 / ppp; ++pass) {
-            const int rr = pass * ppp + pr;                                   // staged row == accumulator row
-            const int gg = rr >> 3, jj = rr & 7;
-            const int ho2 = (sh * 16 + gg) * p.out_s + py, wo2 = (sw * 16 + sub * 8 + jj) * p.out_s + px;
-            const int pc = lc ^ (rr & (chunks16 - 1));
-            uint4 val = *reinterpret_cast<const uint4*>(stg + rr * row_bytes + pc * 16);
-            bf16* dst = outb + (((size_t)n * p.Ho + ho2) * p.Wo + wo2) * p.Cn + c0 + lc * 8;
-            if (p.accumulate) {
+          if (!p.accumulate) {
+            for (int pass = 0; pass < 128 / ppp; pass += 4) {                  // 128/ppp is 8 or 16: four loads in flight, then four stores
+              uint4 val[4]; bf16* dst[4];
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const int rr = (pass + k4) * ppp + pr;
+                const int gg = rr >> 3, jj = rr & 7;
+                const int ho2 = (sh * 16 + gg) * p.out_s + py, wo2 = (sw * 16 + sub * 8 + jj) * p.out_s + px;
+                val[k4] = *reinterpret_cast<const uint4*>(stg + rr * row_bytes + ((lc ^ (rr & (chunks16 - 1))) << 4));
+                dst[k4] = outb + (((size_t)n * p.Ho + ho2) * p.Wo + wo2) * p.Cn + c0 + lc * 8;
+              }
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) *reinterpret_cast<uint4*>(dst[k4]) = val[k4];
+            }
+          } else {
+            for (int pass = 0; pass < 128 / ppp; ++pass) {
+              const int rr = pass * ppp + pr;                                   // staged row == accumulator row
+              const int gg = rr >> 3, jj = rr & 7;
+              const int ho2 = (sh * 16 + gg) * p.out_s + py, wo2 = (sw * 16 + sub * 8 + jj) * p.out_s + px;
+              const int pc = lc ^ (rr & (chunks16 - 1));
+              uint4 val = *reinterpret_cast<const uint4*>(stg + rr * row_bytes + pc * 16);
+              bf16* dst = outb + (((size_t)n * p.Ho + ho2) * p.Wo + wo2) * p.Cn + c0 + lc * 8;
               float a[8], e[8];
               const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
 #pragma unroll
@@ -288,8 +322,6 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
 #pragma unroll
               for (int i = 0; i < 8; ++i) a[i] += e[i];
               Vec8<bf16>::store(dst, a);
-            } else {
-              *reinterpret_cast<uint4*>(dst) = val;
             }
           }
         }

@@ -307,21 +307,31 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
               for (int k4 = 0; k4 < 4; ++k4) *reinterpret_cast<uint4*>(dst[k4]) = val[k4];
             }
           } else {
-            for (int pass = 0; pass < 128 / ppp; ++pass) {
-              const int rr = pass * ppp + pr;                                   // staged row == accumulator row
-              const int gg = rr >> 3, jj = rr & 7;
-              const int ho2 = (sh * 16 + gg) * p.out_s + py, wo2 = (sw * 16 + sub * 8 + jj) * p.out_s + px;
-              const int pc = lc ^ (rr & (chunks16 - 1));
-              uint4 val = *reinterpret_cast<const uint4*>(stg + rr * row_bytes + pc * 16);
-              bf16* dst = outb + (((size_t)n * p.Ho + ho2) * p.Wo + wo2) * p.Cn + c0 + lc * 8;
-              float a[8], e[8];
-              const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
+            // accumulate into the existing gradient: four read-modify-writes in flight per thread (the global loads dominate)
+            for (int pass = 0; pass < 128 / ppp; pass += 4) {
+              uint4 val[4], old[4]; bf16* dst[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) { const float2 t2 = __bfloat1622float2(hv[i]); a[2 * i] = t2.x; a[2 * i + 1] = t2.y; }
-              Vec8<bf16>::load(dst, e);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const int rr = (pass + k4) * ppp + pr;
+                const int gg = rr >> 3, jj = rr & 7;
+                const int ho2 = (sh * 16 + gg) * p.out_s + py, wo2 = (sw * 16 + sub * 8 + jj) * p.out_s + px;
+                dst[k4] = outb + (((size_t)n * p.Ho + ho2) * p.Wo + wo2) * p.Cn + c0 + lc * 8;
+                old[k4] = *reinterpret_cast<const uint4*>(dst[k4]);
+                val[k4] = *reinterpret_cast<const uint4*>(stg + rr * row_bytes + ((lc ^ (rr & (chunks16 - 1))) << 4));
+              }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] += e[i];
-              Vec8<bf16>::store(dst, a);
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val[k4]);
+                const __nv_bfloat162* ho_ = reinterpret_cast<const __nv_bfloat162*>(&old[k4]);
+                uint4 r;
+                __nv_bfloat162* hr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 a = __bfloat1622float2(hv[i]), b = __bfloat1622float2(ho_[i]);
+                  hr[i] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+                }
+                *reinterpret_cast<uint4*>(dst[k4]) = r;
+              }
             }
           }
         }

@@ -189,6 +189,54 @@ def classify_step(tr, steps, layers=None):
     return agg
 
 
+def conv_class_time(tr, reps=5):
+    """Device time of ALL tensor-core conv launches of one step (fprop, dgrad, wgrad; the other kernels skipped), issued back to back
+    between two CUDA events on the launch stream.  Buffers are static, so the sequence is valid on its own; the ~1 GB of activations it
+    walks exceeds the 126 MB L2.  Returns (ms per step, flops per step, launches per step)."""
+    import torch
+    from awr_b200 import _lib as L
+    pl = tr.plan
+    seq = [(f, m) for f, m in list(zip(pl.fwd, pl.fwd_meta)) + list(zip(pl.bwd, pl.bwd_meta)) if m[0].startswith("conv_")]
+    s = L.stream()
+    for f, _ in seq:
+        f(s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(20e6))
+    e0.record()
+    for _ in range(reps):
+        for f, _m in seq:
+            f(s)
+    e1.record()
+    torch.cuda.synchronize()
+    tr.store.grads.zero_()
+    return e0.elapsed_time(e1) / reps, sum(m[1] for _, m in seq), len(seq)
+
+
+def head_pair_time(tr, reps=8):
+    """Cold-cache device time of the fused head+loss forward + backward kernels (L2 flushed by a 512 MB fill before every pair)."""
+    import torch
+    from awr_b200 import _lib as L
+    pl, hd, lib = tr.plan, tr.head, tr.lib
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=tr.device)
+    tot = 0.0
+    for _ in range(reps):
+        torch.cuda._sleep(int(4e6))
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s = L.stream()
+        e0.record()
+        L.check(lib.awr_head_fwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), tr.jt.data_ptr(), tr.uvd.data_ptr(), tr.loss.data_ptr(),
+                                 tr.ws.data_ptr(), tr.B, tr.J, tr.F, tr.H, tr.ks, s), "head_fwd")
+        L.check(lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), tr.jt.data_ptr(), tr.uvd.data_ptr(), tr.ws.data_ptr(), None, None,
+                                 hd.dpred.data_ptr(), tr.B, tr.J, tr.F, tr.H, tr.ks, tr.cw, tr.dw, s), "head_bwd")
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    del flush
+    return tot / reps
+
+
 def main():
     global H, METRIC
     a = parse()
@@ -297,19 +345,22 @@ def main():
         tot = sum(v[0] for v in agg.values())
         classes = {k: {"ms_per_step": round(v[0] / 3, 4), "share": round(v[0] / tot, 4), "launches_per_step": v[3] // 3} for k, v in
                    sorted(agg.items(), key=lambda kv: -kv[1][0])}
-        conv = [v for k, v in agg.items() if k.startswith("conv_")]
-        cms, cfl, cn = sum(v[0] for v in conv), sum(v[1] for v in conv), sum(v[3] for v in conv)
+        # dominant kernel class: the tcgen05 implicit-GEMM convolutions, timed back to back (no per-launch event overhead)
+        cms, cfl, cn = conv_class_time(tr)
         ach = cfl / (cms * 1e-3) / 1e12
-        roof = {"kernel": "conv/deconv implicit-GEMM (fprop+dgrad+wgrad)", "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sust"],
-                "unit": "TFLOP/s", "frac": round(ach / pk["tf_sust"], 4), "traffic": None, "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
-                "launches_per_step": cn // 3, "avg_launch_us": round(1e3 * cms / cn, 2), "share_of_step": round(cms / tot, 4),
-                "flops_per_step": cfl // 3}
+        roof = {"kernel": "tcgen05 conv/deconv implicit-GEMM kernels (conv_halo_kernel, conv_tc_kernel, wgrad_tc_kernel: fprop+dgrad+wgrad)",
+                "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sust"], 4),
+                "traffic": None, "peak_source": pk["src"] + " (sustained cuBLAS bf16 8192^3)", "launches_per_step": cn,
+                "avg_launch_us": round(1e3 * cms / cn, 2), "ms_per_step": round(cms, 4), "share_of_step": round(cms / (ms / a.steps), 4),
+                "flops_per_step": cfl, "how": "all conv launches of one step issued back to back between two CUDA events, 5 repetitions"}
         hv = [agg["head_fwd"], agg["head_bwd"]]
-        hms, hb = sum(v[0] for v in hv), sum(v[2] for v in hv)
+        hb = sum(v[2] for v in hv) // 3
+        hms = head_pair_time(tr)
         hach = hb / (hms * 1e-3) / 1e9
-        roof_head = {"kernel": "fused AWR head+loss (fwd, bwd)", "bound": "hbm", "achieved": round(hach, 1), "peak": pk["hbm"], "unit": "GB/s",
-                     "frac": round(hach / pk["hbm"], 4), "traffic": None, "peak_source": pk["src"] + " (copy)",
-                     "avg_launch_us": round(1e3 * hms / 6, 2), "bytes_per_step": hb // 3, "share_of_step": round(hms / tot, 4)}
+        roof_head = {"kernel": "fused AWR head+loss (head_fwd_kernel + head_bwd_kernel)", "bound": "hbm", "achieved": round(hach, 1), "peak": pk["hbm"],
+                     "unit": "GB/s", "frac": round(hach / pk["hbm"], 4), "traffic": 61054976, "peak_source": pk["src"] + " (copy)",
+                     "pair_us": round(1e3 * hms, 2), "bytes_per_step": hb, "how": "cold L2 (512 MB fill before each fwd+bwd pair), 8 repetitions; "
+                     "traffic = ncu dram bytes of the pair (profiles/r01_final_head_full.md)"}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------
     cpu = None

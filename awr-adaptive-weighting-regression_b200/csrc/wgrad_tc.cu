@@ -29,6 +29,11 @@ constexpr int kThreads = 192;
 constexpr int kMaxMTiles = 5;
 constexpr int kMaxGroups = 9;
 
+// 16-byte vector reduction (sm_90+): one L2 atomic transaction for four consecutive floats
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct MTile {
   int tap[2];            // weight tap of each 64-row block
   int ch[2];             // gathered-channel offset (within the CTA's channel block) of each 64-row block
@@ -156,27 +161,39 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(t_addr + ch, v);
           tmem_ld_wait();
-          if (p.s_p != 1) {
-            // rows (gathered channels) are the contiguous dimension of dW: each column is one coalesced 128-B reduction per warp
-            if (valid) {
+          // The warp's 32x32 fp32 block goes through shared memory (pipeline stages are idle by now) so that each lane owns FOUR
+          // consecutive elements along the contiguous dimension of dW and one red.global.add.v4.f32 covers 16 bytes: a quarter of the
+          // reduction instructions, every one on whole 128-B lines.  tb[row][col], row = gathered channel (this lane), col = pointwise ch.
+          float* tb = reinterpret_cast<float*>(smem_al) + q * (32 * 36);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) atomicAdd(base + (size_t)(ch + i) * p.s_p, __uint_as_float(v[i]));
-            }
-          } else {
-            // columns (pointwise channels) are contiguous in dW (ConvTranspose2d layout): transpose the warp's 32x32 block through
-            // shared memory (the pipeline stages are idle by now) so every reduction instruction again covers one 128-B line
-            float* tb = reinterpret_cast<float*>(smem_al) + q * (32 * 33);
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(tb + lane * 36 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                                                         __uint_as_float(v[i + 3]));
+          __syncwarp();
+          const int r0 = q * 32, bk = r0 >> 6;                    // the warp's 32 rows lie inside one 64-row block
+          if (bk == 0 || T.valid1) {
+            float* wbase = dW + (size_t)T.tap[bk] * p.w_tap + (size_t)(cg0 + T.ch[bk] + (r0 & 63)) * p.s_g + (size_t)(nt * p.Ntile + ch) * p.s_p;
+            if (p.s_p == 1) {
+              // columns contiguous (ConvTranspose2d layout): lane -> (row rr0 + lane/8, cols 4*(lane%8)..+3), 8 iterations of 4 rows
+              const int cq = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) tb[lane * 33 + i] = __uint_as_float(v[i]);
-            __syncwarp();
-            const int r0 = q * 32;
-            for (int rr = 0; rr < 32; ++rr) {
-              const int rw = r0 + rr, bk = rw >> 6, jj = rw & 63;
-              if (bk == 0 || T.valid1)
-                atomicAdd(dW + (size_t)T.tap[bk] * p.w_tap + (size_t)(cg0 + T.ch[bk] + jj) * p.s_g + (size_t)(nt * p.Ntile + ch + lane), tb[rr * 33 + lane]);
+              for (int it8 = 0; it8 < 8; ++it8) {
+                const int rr = it8 * 4 + rsub;
+                const float4 x = *reinterpret_cast<const float4*>(tb + rr * 36 + cq);
+                red_add_v4(wbase + (size_t)rr * p.s_g + cq, x);
+              }
+            } else {
+              // rows contiguous (Conv2d layout, s_g == 1): lane -> (col cc0 + lane/8, rows 4*(lane%8)..+3)
+              const int rq = (lane & 7) * 4, csub = lane >> 3;
+#pragma unroll
+              for (int it8 = 0; it8 < 8; ++it8) {
+                const int cc = it8 * 4 + csub;
+                const float4 x = make_float4(tb[rq * 36 + cc], tb[(rq + 1) * 36 + cc], tb[(rq + 2) * 36 + cc], tb[(rq + 3) * 36 + cc]);
+                red_add_v4(wbase + (size_t)cc * p.s_p + rq, x);
+              }
             }
-            __syncwarp();
           }
+          __syncwarp();
         }
       }
     }
@@ -194,6 +211,7 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
                       int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream) {
   AWR_HOST_CHECK(pointwise && gathered && dW && N > 0 && Cp % 64 == 0 && Cg % 64 == 0 && (Cg == 64 || Cg % 128 == 0));
   AWR_HOST_CHECK(R > 0 && S > 0 && R * S <= 16 && (stride == 1 || stride == 2));
+  AWR_HOST_CHECK((s_p == 1 && s_g % 4 == 0) || (s_g == 1 && s_p % 4 == 0));      // 16-byte vector reductions need one contiguous dimension
   AWR_HOST_CHECK(is_pow2(Wc) && is_pow2(Hc) && Wc <= 256 && Hc <= 256);
   WgradParams p;
   memset(&p, 0, sizeof(p));

@@ -246,9 +246,63 @@ class Plan:
             self._build_hourglass(int(n))
         else:
             raise ValueError(net)
+        self.bwd_split = None          # (launch index, flat gradient offset): gradients at/after the offset are final after that many launches
         if training:
-            for op in reversed(self.ops):
-                op.plan_bwd()
+            marks = {}
+            for i in range(len(self.ops) - 1, -1, -1):
+                self.ops[i].plan_bwd()
+                marks[i] = len(self.bwd)
+            self._find_bwd_split(marks)
+
+    def _op_param_names(self, op):
+        names = []
+        for attr in ("wname", "bname"):
+            n = getattr(op, attr, None)
+            if n:
+                names.append(n)
+        for attr in ("prefix", "res_prefix"):
+            n = getattr(op, attr, None)
+            if n:
+                names += [n + ".weight", n + ".bias"]
+        g = getattr(op, "gname", None)
+        if g:
+            names += [g + ".weight", g + ".bias"]
+        return names
+
+    def _find_bwd_split(self, marks):
+        """Early gradient bucket for overlapping the data-parallel all-reduce with the rest of backward: the latest ops (head, deconvs,
+        last stage) hold most parameters and finish their gradients first.  Picks the op suffix whose parameters are a contiguous tail
+        of the flat buffer covering ~80 % of it."""
+        lay = self.store.layout
+
+        def span(name):
+            if name in lay.groups:
+                off, shp = lay.groups[name]
+                return off, off + int(math.prod(shp))
+            sp = lay.specs[name]
+            return sp.offset, sp.offset + sp.numel
+        total, best = lay.total, None
+        lo = total
+        for i in range(len(self.ops) - 1, 0, -1):
+            for n in self._op_param_names(self.ops[i]):
+                lo = min(lo, span(n)[0])
+            # every parameter at or beyond `lo` must belong to ops >= i
+            ok = True
+            for j in range(i):
+                for n in self._op_param_names(self.ops[j]):
+                    if span(n)[1] > lo:
+                        ok = False
+                        break
+                if not ok:
+                    break
+            frac = (total - lo) / total
+            if ok and frac >= 0.5:
+                if best is None or abs(frac - 0.8) < abs(best[2] - 0.8):
+                    best = (marks[i], lo, frac)
+            if frac > 0.95:
+                break
+        if best is not None and 0 < best[0] < len(self.bwd):
+            self.bwd_split = (best[0], best[1])
 
     # ---- infrastructure ---------------------------------------------------------------------------
     def arena(self, n):
@@ -292,17 +346,20 @@ class Plan:
         for f in self.fwd:
             f(s)
 
-    def run_backward(self, stream=None, side=None):
+    def run_backward(self, stream=None, side=None, part=None):
         """side: optional torch.cuda.Stream.  Launches flagged `side` (weight gradients) are issued there, each after everything
         enqueued so far on the main stream (its inputs), and the main stream joins the side stream at the end.  Works eagerly and
         under CUDA-graph capture (the fork/join events become graph edges)."""
         s = L.stream() if stream is None else stream
+        lo, hi = 0, len(self.bwd)
+        if part is not None and self.bwd_split is not None:        # part 0: launches before the split, part 1: the rest
+            lo, hi = (0, self.bwd_split[0]) if part == 0 else (self.bwd_split[0], len(self.bwd))
         if side is None:
-            for f in self.bwd:
+            for f in self.bwd[lo:hi]:
                 f(s)
             return
         main = torch.cuda.current_stream()
-        for f, on_side in zip(self.bwd, self.bwd_side):
+        for f, on_side in list(zip(self.bwd, self.bwd_side))[lo:hi]:
             if on_side:
                 side.wait_stream(main)
                 f(side.cuda_stream)

@@ -12,6 +12,8 @@ Semantics kept from train.py: loss = coord_weight*SmoothL1(uvd, jt) + dense_weig
 (:119-120); for 'hourglass_N' only the last stack is supervised (:116-121 overwrite `loss`); Adam(lr, betas
 (0.9,0.999), eps 1e-8, weight_decay) (:67); BN statistics are per replica (the reference has no SyncBN).
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -58,8 +60,12 @@ class FusedTrainer:
         self.launches_per_step = len(self.plan.fwd) + len(self.plan.bwd) + 2 + 2
 
     # ---- launch sequences -------------------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd(self, part=None):
+        """part None: whole forward+backward; 0: forward + head + backward up to the gradient-bucket split; 1: rest of backward."""
         pl, st, s = self.plan, self.store, L.stream()
+        if part == 1:
+            pl.run_backward(s, side=self.side, part=1)
+            return
         pl.arena_buf.zero_()
         st.grads.zero_()
         for h in pl.heads[:-1]:
@@ -71,7 +77,7 @@ class FusedTrainer:
         L.check(self.lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), self.uvd.data_ptr(),
                                       self.ws.data_ptr(), None, None, hd.dpred.data_ptr(), self.B, self.J, self.F, self.H, self.ks,
                                       self.cw, self.dw, s), "awr_head_bwd")
-        pl.run_backward(s, side=self.side)
+        pl.run_backward(s, side=self.side, part=part)
 
     def _opt(self):
         st, s = self.store, L.stream()
@@ -85,6 +91,19 @@ class FusedTrainer:
         if self.world > 1:
             dp.allreduce_sum_(self.store.grads, self.pg)        # NCCL over NVLink; 1/world is applied inside awr_adam_flat
 
+    def _overlapped(self):
+        """Data-parallel step with the all-reduce of the early gradient bucket (last layers: most of the bytes) overlapping the rest of
+        backward: graph A -> async NCCL on bucket 1 -> graph B -> async NCCL on bucket 0 -> wait both -> Adam graph."""
+        import torch.distributed as dist
+        off = self.plan.bwd_split[1]
+        g = self.store.grads
+        self.graph_fb.replay()
+        w1 = dist.all_reduce(g[off:], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self.graph_fb2.replay()
+        w0 = dist.all_reduce(g[:off], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        w1.wait(); w0.wait()
+        self.graph_opt.replay()
+
     def _capture(self):
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
@@ -92,9 +111,18 @@ class FusedTrainer:
             self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self.split = self.world > 1 and self.plan.bwd_split is not None and os.environ.get("AWR_B200_NO_OVERLAP") != "1"
         self.graph_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_fb):
-            self._fwd_bwd()
+        self.graph_fb2 = None
+        if self.split:
+            with torch.cuda.graph(self.graph_fb):
+                self._fwd_bwd(part=0)
+            self.graph_fb2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_fb2):
+                self._fwd_bwd(part=1)
+        else:
+            with torch.cuda.graph(self.graph_fb):
+                self._fwd_bwd()
         self.graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_opt):
             self._opt()
@@ -111,9 +139,12 @@ class FusedTrainer:
         if self.use_graph:
             if self.graph_fb is None:
                 self._capture()
-            self.graph_fb.replay()
-            self._allreduce()
-            self.graph_opt.replay()
+            if self.split:
+                self._overlapped()
+            else:
+                self.graph_fb.replay()
+                self._allreduce()
+                self.graph_opt.replay()
         else:
             self._fwd_bwd()
             self._allreduce()

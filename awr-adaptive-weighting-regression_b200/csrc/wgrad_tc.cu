@@ -78,8 +78,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
   const int pb0 = ks * per, pb1 = min(p.pix_blocks, pb0 + per);
   const int iters = max(pb1 - pb0, 0);
   const int hbytes = G.pw * G.hrows * 128;
-  // the gathered tensor map of this group (box shape depends on the group's halo extents): groups are numbered so that
-  // groups with equal box shape share a map index (host fills map_of_group in halo_ox's upper bits -> kept simple: gi & 3)
+  // the gathered tensor map of this group (box shape depends on the group's halo extents); slot = gi & 3, the host checks that
+  // groups beyond the fourth repeat the box shape of group gi - 4
   const CUtensorMap* tmG = (gi & 3) == 0 ? &tmG0 : ((gi & 3) == 1 ? &tmG1 : ((gi & 3) == 2 ? &tmG2 : &tmG3));
 
   if (threadIdx.x == 0) {
@@ -148,14 +148,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
   } else {
     // ======================================= epilogue =======================================
     const int q = warp & 3;
-    const int row = q * 32 + lane, blk = row >> 6, j = row & 63;
     mbar_wait(&tfull_bar, 0);
     tc_fence_after();
     if (iters > 0) {
       for (int m = 0; m < G.n_mtiles; ++m) {
         const MTile& T = G.mt[m];
-        const bool valid = (blk == 0 || T.valid1);
-        float* base = dW + (size_t)T.tap[blk] * p.w_tap + (size_t)(cg0 + T.ch[blk] + j) * p.s_g + (size_t)(nt * p.Ntile) * p.s_p;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * p.Ntile);
         for (int ch = 0; ch < p.Ntile; ch += 32) {
           uint32_t v[32];
@@ -245,8 +242,6 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
       cls[c][ncls[c]++] = TapI{r, s, (ty - cy) / stride, (tx - cx) / stride};
     }
   int ng = 0;
-  int map_box[4][2]; int nmaps = 0;            // distinct (pw, hrows) box shapes -> at most 4 tensor maps
-  int group_cls[kMaxGroups];
   for (int c = 0; c < nclass; ++c) {
     if (ncls[c] == 0) continue;
     // taps per group: as many as fit TMEM; groups are cut at tap-row boundaries when a whole class does not fit
@@ -287,7 +282,6 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
         } else { T.tap[1] = T.tap[0]; T.aoff[1] = -1; T.ch[1] = 64; T.valid1 = 1; }   // second channel block: fixed up below
       }
       G.n_mtiles = m;
-      group_cls[ng] = c;
       ++ng;
       start = end;
     }
@@ -297,7 +291,6 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
   for (int g = 0; g < ng; ++g)
     for (int m = 0; m < p.grp[g].n_mtiles; ++m)
       if (p.grp[g].mt[m].aoff[1] < 0) p.grp[g].mt[m].aoff[1] = p.grp[g].mt[m].aoff[0] + p.halo_block_bytes;
-  (void)group_cls;
 
   // ---- tensor maps: one per group slot (gi & 3); groups beyond 4 must repeat the box shape of group gi-4 ---------------
   CUtensorMap tmG[4], tmP;

@@ -12,7 +12,7 @@
 // weight tile: per (tap, 64-channel block) ONE B tile feeds 8 MMAs (2 sub-tiles x K=64), halving weight traffic per FLOP.
 // Accumulators: 2 TMEM stages x 2 sub-tiles x Ntile (<=128) fp32 columns.  Epilogue: TMEM -> registers -> (+bias) -> bf16 ->
 // swizzled smem staging tile -> (a) per-channel sum / sum-of-squares for BatchNorm read column-wise from smem, (b) fully
-// coalesced NHWC stores (optionally accumulating).  Roles: warps 0-3 epilogue, warp 4 TMA producer, warp 5 MMA issuer (the SM arbiter favours
+// coalesced NHWC stores (optionally accumulating).  Roles: warps 0-7 epilogue (two groups of four, one per sub-tile), warp 8 TMA producer, warp 9 MMA issuer (the SM arbiter favours
 // higher warp ids, so the two latency-critical single-lane roles sit above the ALU-heavy epilogue warps).
 //
 // Handles every unit-stride gather: stride-1 Conv2d fprop/dgrad, ConvTranspose2d(k4,s2,p1) fprop parity classes, stride-2 Conv2d
@@ -25,7 +25,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                 // 8 epilogue warps (two groups, one per sub-tile) + TMA producer warp + MMA issuer warp
 constexpr int kHaloStageBytes = 44032;       // >= 18*18 rows * 128 B, multiple of 1024
 constexpr int kHaloStages = 2;
 
@@ -56,7 +56,7 @@ __device__ unsigned long long g_halo_prof[148 * 16];
 #define HPROF_ADD(slot)
 #endif
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }   // one named barrier per epilogue group
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
@@ -75,7 +75,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
   const int b_bytes = p.Ntile * 128;
   const uint32_t b_base = smem_base + kHaloStages * kHaloStageBytes;
   const uint32_t stg_base = b_base + (uint32_t)(p.b_stages * b_bytes);            // staging tile [128][Ntile] bf16 (1024-aligned)
-  float* s_stats = reinterpret_cast<float*>(smem_al + (stg_base - smem_base) + 128 * p.Ntile * 2);
+  float* s_stats = reinterpret_cast<float*>(smem_al + (stg_base - smem_base) + 2 * 128 * p.Ntile * 2);      // behind the two staging tiles
   const int total_items = p.nclasses * p.tiles_c * p.items_m;
   if (stats) {
     for (int i = threadIdx.x; i < 2 * p.Cn; i += kThreads) s_stats[i] = 0.f;
@@ -85,17 +85,17 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kHaloStages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
     for (int i = 0; i < p.b_stages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(&tmem_base_s, 512);
+  if (warp == 9) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();                    // prologue done; from here on the previous kernel's outputs are visible
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       int hs = 0; uint32_t hph = 0; int bs = 0; uint32_t bph = 0;
@@ -127,7 +127,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ======================================= MMA issuer =======================================
     const uint32_t idesc = umma_idesc_bf16(128, p.Ntile, 0, p.b_mn);
     const uint64_t bdesc0 = p.b_mn ? umma_desc_sw128(b_base, 8192, 1024) : umma_desc_sw128(b_base, 16, 1024);
@@ -195,10 +195,12 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
     }
   } else {
     // ======================================= epilogue =======================================
-    const int q = warp & 3;
-    const int et = q * 32 + lane;                 // 0..127: epilogue thread id == accumulator row (TMEM lane)
+    // two epilogue groups of four warps: group `grp` drains sub-tile `grp` (its own staging tile and named barrier), so the two
+    // sub-tiles of a super-tile are converted, reduced and stored concurrently -- the epilogue, not the MMA stream, bounds these kernels
+    const int q = warp & 3, grp = warp >> 2;
+    const int et = q * 32 + lane;                 // 0..127: epilogue thread id within the group == accumulator row (TMEM lane)
     const int g = et >> 3, j = et & 7;            // row = group g (image row h0+g), pixel j inside the group
-    uint8_t* const stg = smem_al + (stg_base - smem_base);
+    uint8_t* const stg = smem_al + (stg_base - smem_base) + grp * (128 * p.Ntile * 2);
     const int row_bytes = p.Ntile * 2, chunks16 = row_bytes >> 4;        // 16-byte chunks per staged row (8 or 16)
     int as = 0; uint32_t aphase = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -209,12 +211,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
       const int c0 = ct * p.Ntile;
       const bool has_acc = p.cls[c].ntaps > 0;
       const int py = p.cls[c].py, px = p.cls[c].px;
-      { HPROF_T0(); mbar_wait(&tfull[as], aphase); if (et == 0) HPROF_ADD(5); }
+      { HPROF_T0(); mbar_wait(&tfull[as], aphase); if (et == 0 && grp == 0) HPROF_ADD(5); }
 #ifdef AWR_CONV_PROFILE
       const long long e_t0 = clock64();
 #endif
       tc_fence_after();
-      for (int sub = 0; sub < 2; ++sub) {
+      {
+        const int sub = grp;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * 2 + sub) * p.Ntile);
         const int hc_ = sh * 16 + g, wc_ = sw * 16 + sub * 8 + j;
         const int ho = hc_ * p.out_s + py, wo = wc_ * p.out_s + px;
@@ -258,13 +261,13 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
             }
           }
         }
-        if (sub == 1) {               // both sub-tiles are out of TMEM: hand the accumulator stage back to the MMA warp
+        {                             // this warp's share of the accumulator stage is out of TMEM: hand it back to the MMA warp (8 arrivals)
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[as]);
         }
-        if (p.out_mode == 1) continue;
-        epi_bar();
+        if (p.out_mode != 1) {
+        epi_bar(grp);
         // (a) BatchNorm statistics: thread -> one column pair, a slice of rows; reads are bank-conflict free
         if (stats) {
           const int pairs = p.Ntile >> 1, slices = 128 / pairs, rows_per = 128 / slices;
@@ -335,10 +338,11 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
             }
           }
         }
-        epi_bar();                    // staging tile free for the next sub-tile
+        epi_bar(grp);                 // staging tile free for the next item
+        }
       }
 #ifdef AWR_CONV_PROFILE
-      if (et == 0) { atomicAdd(&g_halo_prof[blockIdx.x * 16 + 6], (unsigned long long)(clock64() - e_t0)); atomicAdd(&g_halo_prof[blockIdx.x * 16 + 8], 1ull); }
+      if (et == 0 && grp == 0) { atomicAdd(&g_halo_prof[blockIdx.x * 16 + 6], (unsigned long long)(clock64() - e_t0)); atomicAdd(&g_halo_prof[blockIdx.x * 16 + 8], 1ull); }
 #endif
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
@@ -351,7 +355,7 @@ conv_halo_kernel(const __grid_constant__ HaloMaps tmA, const __grid_constant__ C
       if (v != 0.f) atomicAdd(stats + i, v);
     }
   }
-  if (warp == 5) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 9) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 #ifdef AWR_CONV_PROFILE
   if (threadIdx.x == 0) atomicAdd(&g_halo_prof[blockIdx.x * 16 + 7], (unsigned long long)(clock64() - k_t0));
 #endif
@@ -413,7 +417,7 @@ int conv_halo_launch(const ConvGeom& g, const void* in, const void* w, const flo
   for (int c = g.nclasses; c < kConvMaxClasses; ++c) maps.a[c] = maps.a[0];
   CUtensorMap tmB;
   if (!conv_make_weight_map(&tmB, g, w, p.Ntile)) return AWR_ERR_DRIVER;
-  const int b_bytes = p.Ntile * 128, stg_bytes = 128 * p.Ntile * 2, stats_bytes = stats ? 2 * g.Cn * (int)sizeof(float) : 0;
+  const int b_bytes = p.Ntile * 128, stg_bytes = 2 * 128 * p.Ntile * 2, stats_bytes = stats ? 2 * g.Cn * (int)sizeof(float) : 0;
   int bst = (205 * 1024 - kHaloStages * kHaloStageBytes - stg_bytes - stats_bytes) / b_bytes;
   if (bst > 8) bst = 8;
   if (bst < 2) return AWR_ERR_UNSUPPORTED;

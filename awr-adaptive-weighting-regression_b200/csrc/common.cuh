@@ -115,3 +115,24 @@ template <> struct Vec8<bf16> {
     *reinterpret_cast<uint4*>(p) = r;
   }
 };
+
+// Raw8<T>: the 8 channels of Vec8<T> as loaded (bf16: one uint4; fp32: two float4), so that a batch of loads can be issued
+// back to back and converted only when consumed.  Bandwidth-bound passes keep U of these per tensor in flight per thread:
+// one 16-byte load per thread at 2-3 resident CTAs/SM is ~12 KB in flight per SM, a third of what HBM3e latency needs.
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};

@@ -7,6 +7,7 @@
 // torch.optim.Adam (train.py:67).
 #include "common.cuh"
 #include "awr_b200.h"
+#include <cstdlib>
 
 namespace {
 
@@ -25,6 +26,19 @@ inline int red_blocks(long long M, int C) {
   if (b < 1) b = 1;
   if (b > 148 * 4) b = 148 * 4;
   return (int)b;
+}
+// grid of the batched-load passes: U items per thread and iteration, at most 4 CTAs per SM in total (2 resident x 2 rounds), a
+// multiple of nothing in particular because total threads only have to be a multiple of G = C/8 <= 256
+inline int ew_grid(long long items, int U) {
+  long long b = (items + (long long)kEwThreads * U - 1) / ((long long)kEwThreads * U);
+  if (b < 1) b = 1;
+  if (b > 148 * 4) b = 148 * 4;
+  return (int)b;
+}
+// loads in flight per thread and tensor of the BatchNorm passes (AWR_EW_UNROLL=1|2|4 overrides; 1 = one 16-byte load at a time)
+inline int ew_unroll() {
+  static const int u = [] { const char* e = getenv("AWR_EW_UNROLL"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
+  return u;
 }
 inline bool chan_ok(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
 
@@ -152,11 +166,11 @@ struct BnSet {
   const float* sums; const float* gamma; const float* beta; float* running_mean; float* running_var; long long* nbt; float* mean_invstd;
 };
 
-__device__ __forceinline__ void bn_coeffs(const BnSet& b, int c, int C, float count, float eps, int training, float& sc, float& sh, float& mean,
+__device__ __forceinline__ void bn_coeffs(const BnSet& b, int c, int C, float inv_count, float eps, int training, float& sc, float& sh, float& mean,
                                           float& invstd, float& var) {
   if (training) {
-    mean = b.sums[c] / count;
-    var = fmaxf(b.sums[C + c] / count - mean * mean, 0.f);
+    mean = b.sums[c] * inv_count;
+    var = fmaxf(b.sums[C + c] * inv_count - mean * mean, 0.f);
   } else {
     mean = b.running_mean[c];
     var = b.running_var[c];
@@ -167,9 +181,10 @@ __device__ __forceinline__ void bn_coeffs(const BnSet& b, int c, int C, float co
 }
 
 __device__ __forceinline__ void bn_side_effects(const BnSet& b, int C, float count, float momentum, float eps, int training) {
+  const float inv_count = 1.0f / count;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float sc, sh, mean, invstd, var;
-    bn_coeffs(b, c, C, count, eps, training, sc, sh, mean, invstd, var);
+    bn_coeffs(b, c, C, inv_count, eps, training, sc, sh, mean, invstd, var);
     if (b.mean_invstd) { b.mean_invstd[c] = mean; b.mean_invstd[C + c] = invstd; }
     if (training && b.running_mean) {
       b.running_mean[c] = (1.f - momentum) * b.running_mean[c] + momentum * mean;
@@ -180,41 +195,55 @@ __device__ __forceinline__ void bn_side_effects(const BnSet& b, int C, float cou
   if (training && b.nbt && threadIdx.x == 0) *b.nbt += 1;
 }
 
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(kEwThreads)
 bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSet rbn, int res_has_bn, T* __restrict__ out, long long M, int C,
               float count, float momentum, float eps, int training, int relu) {
   pdl_entry();
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
-  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  const int c0 = (int)(first % G) * 8;
+  const float inv_count = 1.0f / count;
   float sc[8], sh[8], rsc[8], rsh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     float mean, invstd, var;
-    bn_coeffs(bn, c0 + k, C, count, eps, training, sc[k], sh[k], mean, invstd, var);
-    if (res_has_bn) bn_coeffs(rbn, c0 + k, C, count, eps, training, rsc[k], rsh[k], mean, invstd, var);
+    bn_coeffs(bn, c0 + k, C, inv_count, eps, training, sc[k], sh[k], mean, invstd, var);
+    if (res_has_bn) bn_coeffs(rbn, c0 + k, C, inv_count, eps, training, rsc[k], rsh[k], mean, invstd, var);
   }
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
-    float v[8];
-    Vec8<T>::load(y + i * 8, v);
+  // U items per thread and iteration; every load of the batch is issued before the first use (bytes in flight, see ew_grid)
+  for (long long i0 = first; i0 < items; i0 += U * stride) {
+    Raw8<T> ry[U], rr[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = v[k] * sc[k] + sh[k];
-    if (res) {
-      float r[8];
-      Vec8<T>::load(res + i * 8, r);
-      if (res_has_bn) {
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < items) { ry[u].load(y + i * 8); if (res) rr[u].load(res + i * 8); }
+    }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = r[k] * rsc[k] + rsh[k];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= items) break;
+      float v[8];
+      ry[u].unpack(v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * sc[k] + sh[k];
+      if (res) {
+        float r[8];
+        rr[u].unpack(r);
+        if (res_has_bn) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) r[k] = r[k] * rsc[k] + rsh[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += r[k];
       }
+      if (relu) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += r[k];
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+      Vec8<T>::store(out + i * 8, v);
     }
-    if (relu) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-    }
-    Vec8<T>::store(out + i * 8, v);
   }
   if (blockIdx.x == gridDim.x - 1) {      // side effects after this block's own reads of the running statistics
     __syncthreads();
@@ -239,7 +268,7 @@ bn_relu_maxpool_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ ou
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
   float sc[8], sh[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { float mean, invstd, var; bn_coeffs(bn, c0 + q, C, count, eps, training, sc[q], sh[q], mean, invstd, var); }
+  for (int q = 0; q < 8; ++q) { float mean, invstd, var; bn_coeffs(bn, c0 + q, C, 1.0f / count, eps, training, sc[q], sh[q], mean, invstd, var); }
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
     long long t = i / G;
     const int wo = (int)(t % Wo); t /= Wo;
@@ -262,6 +291,63 @@ bn_relu_maxpool_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ ou
           const float a = from_store<T>(fmaxf(v[q] * sc[q] + sh[q], 0.f));      // the value the unfused path would have stored
           if (a > best[q]) { best[q] = a; bi[q] = (unsigned char)(r * k + c); }
         }
+      }
+    }
+    Vec8<T>::store(out + i * 8, best);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((unsigned)bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((unsigned)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1) { __syncthreads(); bn_side_effects(bn, C, count, momentum, eps, training); }
+}
+
+// 3x3-window specialisation (the ResNet stem, MaxPool(3,2,1)): the nine tap loads of an output pixel are issued back to back from
+// clamped addresses (no data-dependent branches between them) and consumed in the same scan order as above.
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+bn_relu_maxpool3_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ out, unsigned char* __restrict__ idx, int N, int H, int W, int C,
+                            int Ho, int Wo, int s, int p, float count, float momentum, float eps, int training) {
+  pdl_entry();
+  const int G = C >> 3;
+  const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
+  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  const float inv_count = 1.0f / count;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { float mean, invstd, var; bn_coeffs(bn, c0 + q, C, inv_count, eps, training, sc[q], sh[q], mean, invstd, var); }
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    Raw8<T> raw[9];
+    unsigned valid = 0u;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hi = ho * s - p + r, hc = min(max(hi, 0), H - 1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int wi = wo * s - p + c, wc = min(max(wi, 0), W - 1);
+        raw[r * 3 + c].load(y + (((long long)n * H + hc) * W + wc) * C + c0);
+        if (hi == hc && wi == wc) valid |= 1u << (r * 3 + c);
+      }
+    }
+    float best[8];
+    unsigned char bi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bi[q] = 0; }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      if (!((valid >> tap) & 1u)) continue;
+      float v[8];
+      raw[tap].unpack(v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float a = from_store<T>(fmaxf(v[q] * sc[q] + sh[q], 0.f));      // the value the unfused path would have stored
+        if (a > best[q]) { best[q] = a; bi[q] = (unsigned char)tap; }
       }
     }
     Vec8<T>::store(out + i * 8, best);
@@ -343,7 +429,7 @@ maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restri
 // MaxPool(3,2,1) specialisation of maxpool_bn_bwd_kernel (the ResNet stem): one thread owns a 2x2 block of full-resolution pixels
 // (x 8 channels); the four windows that can select any of them are loaded once and scattered with compile-time tap numbers.
 template <typename T>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 2)
 maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restrict__ idx, const T* __restrict__ y,
                          const float* __restrict__ mean_invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                          float* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
@@ -367,17 +453,35 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
     const int j = (int)(t % Wo); t /= Wo;
     const int i = (int)(t % Ho);
     const int n = (int)(t / Ho);
+    // all twelve loads of the block (4 windows x (arg-max bytes + pooled gradient), 4 full-resolution pixels of y) are issued
+    // before the first use; windows past the border are read from the clamped window and ignored
+    uint2 pk[4];
+    Raw8<T> rg[4], ry[4];
+    unsigned wvalid = 0u;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ia = min(i + a, Ho - 1), jb = min(j + b, Wo - 1);
+        const long long o = (((long long)n * Ho + ia) * Wo + jb) * C + c0;
+        pk[a * 2 + b] = *reinterpret_cast<const uint2*>(idx + o);
+        rg[a * 2 + b].load(dpool + o);
+        if (i + a < Ho && j + b < Wo) wvalid |= 1u << (a * 2 + b);
+      }
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) ry[pr * 2 + pc].load(y + (((long long)n * H + 2 * i + pr) * W + 2 * j + pc) * C + c0);
     float dz[4][8] = {};
     // windows (i+a, j+b), a,b in {0,1}: tap hit by block pixel (pr,pc) is (pr+1-2a)*3 + (pc+1-2b) when both factors are in [0,2]
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        if (i + a >= Ho || j + b >= Wo) continue;
-        const long long o = (((long long)n * Ho + i + a) * Wo + j + b) * C + c0;
-        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+        if (!((wvalid >> (a * 2 + b)) & 1u)) continue;
         float g[8];
-        Vec8<T>::load(dpool + o, g);
+        rg[a * 2 + b].unpack(g);
+        const uint2 pkw = pk[a * 2 + b];
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
@@ -387,7 +491,7 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
             const int tap = r * 3 + c;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const unsigned bb = (q < 4) ? ((pk.x >> (8 * q)) & 0xffu) : ((pk.y >> (8 * (q - 4))) & 0xffu);
+              const unsigned bb = (q < 4) ? ((pkw.x >> (8 * q)) & 0xffu) : ((pkw.y >> (8 * (q - 4))) & 0xffu);
               if ((int)bb == tap) dz[pr * 2 + pc][q] += g[q];
             }
           }
@@ -398,7 +502,7 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
       for (int pc = 0; pc < 2; ++pc) {
         const long long pix = (((long long)n * H + 2 * i + pr) * W + 2 * j + pc) * C + c0;
         float yy[8];
-        Vec8<T>::load(y + pix, yy);
+        ry[pr * 2 + pc].unpack(yy);
         float* d = dz[pr * 2 + pc];
 #pragma unroll
         for (int q = 0; q < 8; ++q) d[q] = (from_store<T>(fmaxf(yy[q] * sc[q] + sh[q], 0.f)) > 0.f) ? d[q] : 0.f;
@@ -425,7 +529,7 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
 // ---------------------------------------------------------------------------------------------------------
 // BN backward, pass 1: dz = dout * (act_out > 0 if relu);  dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * yhat
 // ---------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
                      const float* __restrict__ mean_invstd, long long M, int C, float* __restrict__ dsums,
@@ -434,7 +538,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
   __shared__ float smem[kEwThreads * 8];
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
-  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  const int c0 = (int)(first % G) * 8;
   float mean[8], istd[8], msc[8], msh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -442,28 +547,41 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
     if (mask_gamma) { msc[k] = mask_gamma[c0 + k] * istd[k]; msh[k] = mask_beta[c0 + k] - mean[k] * msc[k]; }
   }
   float acc[2][8] = {};
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
-    float g[8], yy[8];
-    Vec8<T>::load(dout + i * 8, g);
-    Vec8<T>::load(y + i * 8, yy);
-    if (mask_gamma) {            // ReLU(BN(y)) without residual: the mask is a function of y alone, no need to read the activation
+  for (long long i0 = first; i0 < items; i0 += U * stride) {
+    Raw8<T> rg[U], ry[U], ra[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = (from_store<T>(fmaxf(yy[k] * msc[k] + msh[k], 0.f)) > 0.f) ? g[k] : 0.f;
-    } else if (act_out) {
-      float a[8];
-      Vec8<T>::load(act_out + i * 8, a);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < items) {
+        rg[u].load(dout + i * 8); ry[u].load(y + i * 8);
+        if (!mask_gamma && act_out) ra[u].load(act_out + i * 8);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { acc[0][k] += g[k]; acc[1][k] += g[k] * (yy[k] - mean[k]) * istd[k]; }
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= items) break;
+      float g[8], yy[8];
+      rg[u].unpack(g); ry[u].unpack(yy);
+      if (mask_gamma) {          // ReLU(BN(y)) without residual: the mask is a function of y alone, no need to read the activation
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = (from_store<T>(fmaxf(yy[k] * msc[k] + msh[k], 0.f)) > 0.f) ? g[k] : 0.f;
+      } else if (act_out) {
+        float a[8];
+        ra[u].unpack(a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[0][k] += g[k]; acc[1][k] += g[k] * (yy[k] - mean[k]) * istd[k]; }
+    }
   }
   block_channel_reduce<2>(acc, G, C, dsums, smem);
 }
 
 // pass 2: dy = gamma*invstd*(dz - mean(dz) - yhat*mean(dz*yhat));  optional dres = dz (gradient of the residual branch);
-// block 0 also writes dgamma / dbeta.
-template <typename T>
+// block 0 also writes dgamma / dbeta.  dy may alias dy_addend and dres may alias dres_addend (read-modify-write of thread-private
+// items: every load of a batch precedes its stores).
+template <typename T, int U>
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
                     const float* __restrict__ mean_invstd, const float* __restrict__ dsums, const float* __restrict__ gamma,
@@ -472,7 +590,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
   pdl_entry();
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
-  const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
+  const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  const int c0 = (int)(first % G) * 8;
   const float invM = 1.0f / (float)M;
   float mean[8], istd[8], k1[8], k2[8], gs[8], msh[8];
 #pragma unroll
@@ -481,38 +600,54 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
     k1[k] = dsums[c0 + k] * invM; k2[k] = dsums[C + c0 + k] * invM; gs[k] = gamma[c0 + k] * istd[k];
     msh[k] = mask_beta ? mask_beta[c0 + k] - mean[k] * gs[k] : 0.f;
   }
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
-    float g[8], yy[8];
-    Vec8<T>::load(dout + i * 8, g);
-    Vec8<T>::load(y + i * 8, yy);
-    if (mask_beta) {
+  const bool use_act = !mask_beta && act_out, add_res = dres && dres_addend;
+  for (long long i0 = first; i0 < items; i0 += U * stride) {
+    Raw8<T> rg[U], ry[U], ra[U], rb[U], rc[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = (from_store<T>(fmaxf(yy[k] * gs[k] + msh[k], 0.f)) > 0.f) ? g[k] : 0.f;
-    } else if (act_out) {
-      float a[8];
-      Vec8<T>::load(act_out + i * 8, a);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
-    }
-    float o[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = gs[k] * (g[k] - k1[k] - (yy[k] - mean[k]) * istd[k] * k2[k]);
-    if (dres) {
-      if (dres_addend) {
-        float b[8];
-        Vec8<T>::load(dres_addend + i * 8, b);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] += b[k];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < items) {
+        rg[u].load(dout + i * 8); ry[u].load(y + i * 8);
+        if (use_act) ra[u].load(act_out + i * 8);
+        if (add_res) rb[u].load(dres_addend + i * 8);
+        if (dy_addend) rc[u].load(dy_addend + i * 8);
       }
-      Vec8<T>::store(dres + i * 8, g);
     }
-    if (dy_addend) {
-      float b[8];
-      Vec8<T>::load(dy_addend + i * 8, b);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] += b[k];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= items) break;
+      float g[8], yy[8];
+      rg[u].unpack(g); ry[u].unpack(yy);
+      if (mask_beta) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = (from_store<T>(fmaxf(yy[k] * gs[k] + msh[k], 0.f)) > 0.f) ? g[k] : 0.f;
+      } else if (act_out) {
+        float a[8];
+        ra[u].unpack(a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+      }
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = gs[k] * (g[k] - k1[k] - (yy[k] - mean[k]) * istd[k] * k2[k]);
+      if (dres) {
+        if (dres_addend) {
+          float b[8];
+          rb[u].unpack(b);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g[k] += b[k];
+        }
+        Vec8<T>::store(dres + i * 8, g);
+      }
+      if (dy_addend) {
+        float b[8];
+        rc[u].unpack(b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += b[k];
+      }
+      Vec8<T>::store(dy + i * 8, o);
     }
-    Vec8<T>::store(dy + i * 8, o);
   }
   if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += kEwThreads) {
@@ -698,6 +833,34 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
     if (p < P && c < Cdst) dst[((long long)n * P + p) * Cdst + c] = from_f<T>(tile[threadIdx.x][r]);
   }
 }
+// same conversion for Cdst % 8 == 0 (the head gradient d pred: 4J fp32 planes -> 64 bf16 channels): a CTA moves 64 pixels x 64 channels,
+// 16 independent coalesced plane loads per thread, then one 8-channel vector store per thread (4 pixels x 128 B contiguous per warp)
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_vec_kernel(const float* __restrict__ src, T* __restrict__ dst, int Csrc, int Cdst, int P) {
+  pdl_entry();
+  __shared__ float tile[64][65];
+  const int n = blockIdx.z, p0 = blockIdx.x * 64, cb = blockIdx.y * 64;
+  const int px = threadIdx.x & 63, crow = threadIdx.x >> 6;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int c = cb + crow + 4 * k;
+    v[k] = (c < Csrc && p0 + px < P) ? __ldg(src + ((long long)n * Csrc + c) * P + p0 + px) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) tile[crow + 4 * k][px] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int item = threadIdx.x + 256 * h, q = item >> 3, g = item & 7;
+    if (p0 + q < P && cb + g * 8 < Cdst) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = tile[g * 8 + k][q];
+      Vec8<T>::store(dst + ((long long)n * P + p0 + q) * Cdst + cb + g * 8, o);
+    }
+  }
+}
 // src NHWC T (N,P,Csrc) -> dst NCHW fp32 (N,Cdst,P) taking the first Cdst channels
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int Csrc, int Cdst, int P) {
@@ -767,6 +930,21 @@ __global__ void __launch_bounds__(kEwThreads) cast_f32_to_bf16_kernel(const floa
 
 }  // namespace
 
+// T and the load-batch depth U (fp32 rows are 32 bytes: U is capped at 2 there)
+#define DISPATCH_TU(dtype, ...)                                                                    \
+  {                                                                                                \
+    const int u__ = ew_unroll();                                                                   \
+    if ((dtype) == AWR_DTYPE_F32) {                                                                \
+      typedef float T;                                                                             \
+      if (u__ == 1) { constexpr int U = 1; __VA_ARGS__; } else { constexpr int U = 2; __VA_ARGS__; } \
+    } else if ((dtype) == AWR_DTYPE_BF16) {                                                        \
+      typedef bf16 T;                                                                              \
+      if (u__ == 1) { constexpr int U = 1; __VA_ARGS__; }                                          \
+      else if (u__ == 2) { constexpr int U = 2; __VA_ARGS__; }                                     \
+      else { constexpr int U = 4; __VA_ARGS__; }                                                   \
+    } else return AWR_ERR_UNSUPPORTED;                                                             \
+  }
+
 #define DISPATCH_T(dtype, ...)                                             \
   if ((dtype) == AWR_DTYPE_F32) { typedef float T; __VA_ARGS__; }          \
   else if ((dtype) == AWR_DTYPE_BF16) { typedef bf16 T; __VA_ARGS__; }     \
@@ -803,8 +981,8 @@ int awr_bn_act(const void* y, const float* sums, const float* gamma, const float
   AWR_HOST_CHECK(!res_has_bn || (res && res_beta && (training ? (res_sums != nullptr) : (res_running_mean && res_running_var))));
   BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
   BnSet b{res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
-  DISPATCH_T(dtype, launch_pdl(bn_act_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a, (const T*)res, b, res_has_bn, (T*)out, M,
-                                                                                             C, (float)M, momentum, eps, training, relu));
+  DISPATCH_TU(dtype, launch_pdl(bn_act_kernel<T, U>, dim3(ew_grid(M * (C / 8), U)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a,
+                                (const T*)res, b, res_has_bn, (T*)out, M, C, (float)M, momentum, eps, training, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -816,6 +994,12 @@ int awr_bn_relu_maxpool_fwd(const void* y, const float* sums, const float* gamma
   AWR_HOST_CHECK(training ? (sums != nullptr) : (running_mean && running_var));
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
   BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
+  if (k == 3 && ew_unroll() > 1) {
+    DISPATCH_T(dtype, launch_pdl(bn_relu_maxpool3_fwd_kernel<T>, dim3(ew_grid((long long)N * Ho * Wo * (C / 8), 1)), dim3(kEwThreads), 0, (cudaStream_t)stream,
+                          (const T*)y, a, (T*)out, idx, N, H, W, C, Ho, Wo, s, p, (float)((long long)N * H * W), momentum, eps, training));
+    AWR_LAUNCH_CHECK();
+    return AWR_OK;
+  }
   DISPATCH_T(dtype, launch_pdl(bn_relu_maxpool_fwd_kernel<T>, dim3(red_blocks((long long)N * Ho * Wo, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)y, a, (T*)out, idx, N, H, W, C, Ho, Wo, k, s, p, (float)((long long)N * H * W), momentum, eps, training));
   AWR_LAUNCH_CHECK();
@@ -853,7 +1037,7 @@ int awr_affine_act(const void* y, const float* scale_shift, const void* res, con
 int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* mask_gamma,
                       const float* mask_beta, int dtype, long long M, int C, float* dsums, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && M > 0 && chan_ok(C) && ((mask_gamma == nullptr) == (mask_beta == nullptr)));
-  DISPATCH_T(dtype, launch_pdl(bn_bwd_reduce_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
+  DISPATCH_TU(dtype, launch_pdl(bn_bwd_reduce_kernel<T, U>, dim3(ew_grid(M * (C / 8), U)), dim3(kEwThreads), 0, (cudaStream_t)stream,
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, dsums, mask_gamma, mask_beta));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -863,7 +1047,8 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && gamma && dy && M > 0 && chan_ok(C));
-  DISPATCH_T(dtype, launch_pdl(bn_bwd_apply_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
+  // up to five tensors are read per item here: two items per batch keep the kernel at 128 registers = 2 CTAs per SM
+  DISPATCH_TU(dtype, launch_pdl(bn_bwd_apply_kernel<T, (U > 2 ? 2 : U)>, dim3(ew_grid(M * (C / 8), (U > 2 ? 2 : U))), dim3(kEwThreads), 0, (cudaStream_t)stream,
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
                         (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads, mask_beta));
   AWR_LAUNCH_CHECK();
@@ -915,6 +1100,12 @@ int awr_upsample2_bwd(const void* dout, void* dlow, int dtype, int N, int H, int
 
 int awr_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int Csrc, int Cdst, int P, void* stream) {
   AWR_HOST_CHECK(src && dst && N > 0 && Csrc > 0 && Cdst >= Csrc && P > 0);
+  if (Cdst % 8 == 0 && ew_unroll() > 1) {
+    DISPATCH_T(dtype, launch_pdl(nchw_to_nhwc_vec_kernel<T>, dim3((P + 63) / 64, (Cdst + 63) / 64, N), dim3(256), 0, (cudaStream_t)stream, src, (T*)dst,
+                                 Csrc, Cdst, P));
+    AWR_LAUNCH_CHECK();
+    return AWR_OK;
+  }
   dim3 grid((P + 31) / 32, (Cdst + 31) / 32, N), block(32, 8);
   DISPATCH_T(dtype, launch_pdl(nchw_to_nhwc_kernel<T>, dim3(grid), dim3(block), 0, (cudaStream_t)stream, src, (T*)dst, Csrc, Cdst, P));
   AWR_LAUNCH_CHECK();

@@ -7,12 +7,19 @@
 // registers; each (b,j) CTA streams its 4 planes of the prediction volume exactly once.
 #include "common.cuh"
 #include "awr_b200.h"
+#include <cooperative_groups.h>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr float kSoftmaxScale = 30.0f;     // feature_tool.py:60
 constexpr float kDepthBg = 0.99f;          // feature_tool.py:35,57
-constexpr int kHeadThreads = 128;      // 4 CTAs/SM resident -> B*J = 448 CTAs of the headline config run as ONE wave on 148 SMs
+constexpr int kHeadThreads = 128;
+// A (frame, joint) pair is streamed by S CTAs (S = 1, 2 or 4; forward: one thread-block cluster whose online-softmax states are
+// combined through distributed shared memory; backward: independent CTAs).  At the headline size B*J = 448 pairs are only 3 CTAs
+// of 4 warps per SM: S = 2 doubles the loads in flight and evens out the 3-vs-4 CTA imbalance across the 148 SMs.
 
 struct Px4 { float v[4]; };
 
@@ -96,7 +103,7 @@ __device__ void finalize_partials(const float* partial, int nblk, float inv0, fl
 // ------------------------------------------------------------------------------------------------
 // forward: uvd[b,j,:] (+ softmax stats for backward) (+ joint & dense SmoothL1 sums when GT given)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int S>
 __global__ void __launch_bounds__(kHeadThreads, 4)
 head_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const float* __restrict__ jt_gt,
                 float* __restrict__ uvd_out, float* __restrict__ stats, float* __restrict__ partial,
@@ -104,8 +111,9 @@ head_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
   pdl_entry();
   __shared__ float red[6 * 32];
   __shared__ __align__(16) float ax[256];
+  __shared__ float xch[8];               // this CTA's online-softmax state, read by cluster rank 0 when S > 1
   fill_axis(ax, F);
-  const int bj = blockIdx.x, b = bj / J, j = bj - b * J;
+  const int bj = blockIdx.x / S, rank = blockIdx.x - bj * S, b = bj / J, j = bj - b * J;
   const int P = F * F, step = H / F;
   const T* p0 = pred + ((size_t)b * 4 * J + 3 * j) * P;
   const T* ph = pred + ((size_t)b * 4 * J + 3 * J + j) * P;
@@ -152,8 +160,9 @@ head_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
     }
   };
   // two groups per iteration: all 10 loads of both groups are issued before either is consumed (bytes in flight hide HBM latency)
-  int g = threadIdx.x;
-  for (; g + kHeadThreads < ngroups; g += 2 * kHeadThreads) {
+  const int g_hi = (ngroups / S) * (rank + 1);
+  int g = (ngroups / S) * rank + threadIdx.x;
+  for (; g + kHeadThreads < g_hi; g += 2 * kHeadThreads) {
     const int gb = g + kHeadThreads;
     const int ra = g / gpr, ca = (g - ra * gpr) << 2, rb = gb / gpr, cb = (gb - rb * gpr) << 2;
     const int oa = g << 2, ob = gb << 2;
@@ -163,7 +172,7 @@ head_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
     consume(x0a, x1a, x2a, xha, da, ra, ca);
     consume(x0b, x1b, x2b, xhb, db, rb, cb);
   }
-  for (; g < ngroups; g += kHeadThreads) {
+  for (; g < g_hi; g += kHeadThreads) {
     const int r = g / gpr, c = (g - r * gpr) << 2, off = g << 2;
     Px4 x0 = load4<T>(p0 + off), x1 = load4<T>(p0 + P + off), x2 = load4<T>(p0 + 2 * P + off), xh = load4<T>(ph + off);
     Px4 d = load_depth4(img_b, H, step, r, c);
@@ -179,6 +188,33 @@ head_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
   float sc = __expf(mx - bm);            // threads without pixels: exp(-inf) = 0
   float acc[5] = {s * sc, a0 * sc, a1 * sc, a2 * sc, hub};
   block_sum<5>(acc, red);
+  if (S > 1) {
+    // cluster combine: every CTA publishes (max, sum, 3 weighted sums, huber sum); rank 0 merges them in rank order (deterministic)
+    cg::cluster_group cluster = cg::this_cluster();
+    if (threadIdx.x == 0) { xch[0] = bm; xch[1] = acc[0]; xch[2] = acc[1]; xch[3] = acc[2]; xch[4] = acc[3]; xch[5] = acc[4]; }
+    cluster.sync();
+    if (rank == 0 && threadIdx.x == 0) {
+      float st[S][6];
+      float M = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        const float* rx = cluster.map_shared_rank(xch, r);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st[r][k] = rx[k];
+        M = fmaxf(M, st[r][0]);
+      }
+      bm = M;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        const float w = __expf(st[r][0] - M);
+        acc[0] += st[r][1] * w; acc[1] += st[r][2] * w; acc[2] += st[r][3] * w; acc[3] += st[r][4] * w; acc[4] += st[r][5];
+      }
+    }
+    cluster.sync();                      // remote reads of xch are complete before any CTA of the cluster may exit
+    if (rank != 0) return;
+  }
   if (threadIdx.x == 0) {
     float inv = 1.0f / acc[0];
     float o0 = acc[1] * inv, o1 = acc[2] * inv, o2 = acc[3] * inv;
@@ -201,11 +237,11 @@ __global__ void __launch_bounds__(kHeadThreads, 4)
 head_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const float* __restrict__ jt_gt,
                 const float* __restrict__ uvd, const float* __restrict__ stats, const float* __restrict__ g_uvd,
                 const float* __restrict__ loss_grad, float* __restrict__ dpred, int B, int J, int F, int H, float ks,
-                float cw, float dw) {
+                float cw, float dw, int split) {
   pdl_entry();
   __shared__ __align__(16) float ax[256];
   fill_axis(ax, F);
-  const int bj = blockIdx.x, b = bj / J, j = bj - b * J;
+  const int bj = blockIdx.x / split, rank = blockIdx.x - bj * split, b = bj / J, j = bj - b * J;
   const int P = F * F, step = H / F;
   const size_t o0 = ((size_t)b * 4 * J + 3 * j) * P, oh = ((size_t)b * 4 * J + 3 * J + j) * P;
   const float* img_b = img + (size_t)b * H * H;
@@ -253,8 +289,9 @@ head_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
     __stcs(reinterpret_cast<float4*>(dpred + o0 + 2 * P + off), make_float4(r2[0], r2[1], r2[2], r2[3]));
     __stcs(reinterpret_cast<float4*>(dpred + oh + off), make_float4(rh[0], rh[1], rh[2], rh[3]));
   };
-  int g = threadIdx.x;
-  for (; g + kHeadThreads < ngroups; g += 2 * kHeadThreads) {
+  const int g_hi = (ngroups / split) * (rank + 1);
+  int g = (ngroups / split) * rank + threadIdx.x;
+  for (; g + kHeadThreads < g_hi; g += 2 * kHeadThreads) {
     const int gb = g + kHeadThreads;
     const int ra = g / gpr, ca = (g - ra * gpr) << 2, rb = gb / gpr, cb = (gb - rb * gpr) << 2;
     const int oa = g << 2, ob = gb << 2;
@@ -264,7 +301,7 @@ head_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ img, const
     emit(x0a, x1a, x2a, xha, da, ra, ca, oa);
     emit(x0b, x1b, x2b, xhb, db, rb, cb, ob);
   }
-  for (; g < ngroups; g += kHeadThreads) {
+  for (; g < g_hi; g += kHeadThreads) {
     const int r = g / gpr, c = (g - r * gpr) << 2, off = g << 2;
     Px4 x0 = load4<T>(pred + o0 + off), x1 = load4<T>(pred + o0 + P + off), x2 = load4<T>(pred + o0 + 2 * P + off), xh = load4<T>(pred + oh + off);
     Px4 d = load_depth4(img_b, H, step, r, c);
@@ -326,6 +363,38 @@ huber_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dx[i] = k * huber_grad(x[i] - y[i]);
 }
 
+// CTAs per (frame, joint) pair: enough CTAs for ~6 per SM while every thread keeps >= 4 pixel groups.  AWR_HEAD_SPLIT=1|2|4 overrides.
+int head_split(int B, int J, int F) {
+  static const int forced = [] { const char* e = getenv("AWR_HEAD_SPLIT"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
+  if (forced) return forced;
+  const long long pairs = (long long)B * J, groups_per_thread = ((long long)F * F / 4) / kHeadThreads;
+  int S = 1;
+  while (S < 4 && pairs * S < 148 * 6 && groups_per_thread / (2 * S) >= 4) S *= 2;
+  return S;
+}
+
+// forward launch: S-CTA clusters + programmatic dependent launch
+template <typename T, int S>
+cudaError_t launch_head_fwd(cudaStream_t st, const T* pred, const float* img, const float* uvd_gt, float* uvd_out, float* stats, float* partial,
+                            unsigned* counter, float* loss_out, int B, int J, int F, int H, float ks) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * J * S); cfg.blockDim = dim3(kHeadThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = S; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = (S > 1) ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, head_fwd_kernel<T, S>, pred, img, uvd_gt, uvd_out, stats, partial, counter, loss_out, B, J, F, H, ks);
+}
+template <typename T>
+cudaError_t launch_head_fwd_s(int S, cudaStream_t st, const T* pred, const float* img, const float* uvd_gt, float* uvd_out, float* stats,
+                              float* partial, unsigned* counter, float* loss_out, int B, int J, int F, int H, float ks) {
+  if (S == 4) return launch_head_fwd<T, 4>(st, pred, img, uvd_gt, uvd_out, stats, partial, counter, loss_out, B, J, F, H, ks);
+  if (S == 2) return launch_head_fwd<T, 2>(st, pred, img, uvd_gt, uvd_out, stats, partial, counter, loss_out, B, J, F, H, ks);
+  return launch_head_fwd<T, 1>(st, pred, img, uvd_gt, uvd_out, stats, partial, counter, loss_out, B, J, F, H, ks);
+}
+
 bool head_args_ok(int B, int J, int F, int H) { return B > 0 && J > 0 && F >= 4 && F <= 256 && (F % 4) == 0 && H >= F && (H % F) == 0; }
 
 }  // namespace
@@ -340,12 +409,11 @@ int awr_head_fwd(const void* pred, int pred_dtype, const float* img, const float
   float* stats = ws;
   float* partial = ws + 2 * (size_t)B * J;
   unsigned* counter = reinterpret_cast<unsigned*>(ws + 4 * (size_t)B * J);
+  const int S = head_split(B, J, F);
   if (pred_dtype == AWR_DTYPE_F32)
-    launch_pdl(head_fwd_kernel<float>, dim3(B * J), dim3(kHeadThreads), 0, st, (const float*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
-                                                           loss_out, B, J, F, H, kernel_size);
+    launch_head_fwd_s<float>(S, st, (const float*)pred, img, uvd_gt, uvd_out, stats, partial, counter, loss_out, B, J, F, H, kernel_size);
   else if (pred_dtype == AWR_DTYPE_BF16)
-    launch_pdl(head_fwd_kernel<bf16>, dim3(B * J), dim3(kHeadThreads), 0, st, (const bf16*)pred, img, uvd_gt, uvd_out, stats, partial, counter,
-                                                          loss_out, B, J, F, H, kernel_size);
+    launch_head_fwd_s<bf16>(S, st, (const bf16*)pred, img, uvd_gt, uvd_out, stats, partial, counter, loss_out, B, J, F, H, kernel_size);
   else
     return AWR_ERR_UNSUPPORTED;
   AWR_LAUNCH_CHECK();
@@ -358,12 +426,13 @@ int awr_head_bwd(const void* pred, int pred_dtype, const float* img, const float
   AWR_HOST_CHECK(pred && img && uvd && ws && dpred && head_args_ok(B, J, F, H));
   AWR_HOST_CHECK(uvd_gt != nullptr || g_uvd != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
+  const int S = head_split(B, J, F);
   if (pred_dtype == AWR_DTYPE_F32)
-    launch_pdl(head_bwd_kernel<float>, dim3(B * J), dim3(kHeadThreads), 0, st, (const float*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B,
-                                                           J, F, H, kernel_size, coord_weight, dense_weight);
+    launch_pdl(head_bwd_kernel<float>, dim3(B * J * S), dim3(kHeadThreads), 0, st, (const float*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred,
+               B, J, F, H, kernel_size, coord_weight, dense_weight, S);
   else if (pred_dtype == AWR_DTYPE_BF16)
-    launch_pdl(head_bwd_kernel<bf16>, dim3(B * J), dim3(kHeadThreads), 0, st, (const bf16*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred, B, J,
-                                                          F, H, kernel_size, coord_weight, dense_weight);
+    launch_pdl(head_bwd_kernel<bf16>, dim3(B * J * S), dim3(kHeadThreads), 0, st, (const bf16*)pred, img, uvd_gt, uvd, ws, g_uvd, loss_grad, dpred,
+               B, J, F, H, kernel_size, coord_weight, dense_weight, S);
   else
     return AWR_ERR_UNSUPPORTED;
   AWR_LAUNCH_CHECK();

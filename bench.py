@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg (0 disables)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", default="", help="write a per-layer conv timing table to gpurun_out/<name>")
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="also time the oracle's torch ops on this GPU (eager cuDNN/cuBLAS, fp32 and bf16 autocast): a reported bar, never the product")
+    ap.add_argument("--no-parity", action="store_true", help="skip the C1 parity leg (UVD max-abs-diff vs the reference golden vector)")
     return ap.parse_args()
 
 
@@ -80,6 +83,62 @@ def cpu_train_steps(net, ds, ks, batch, steps, warmup=1):
         if it >= warmup:
             times.append(dt)
     return batch * len(times) / sum(times), cores, times
+
+
+def parity_c1(dev):
+    """BASELINE.json configs[0] / the metric's second half: ResNet18-deconv + AWR head, 1x128x128 crop, 14 joints, batch 1, fp32 forward;
+    max |UVD - reference| against the vector the UNMODIFIED reference produced (tests/golden/backbone_cases.pt, case 0).  The oracle is
+    used only to regenerate the seeded state dict and input of that case (checker role)."""
+    import torch
+    import awr_b200
+    from oracle import awr_oracle as O
+    c = torch.load(os.path.join(ROOT, "tests", "golden", "backbone_cases.pt"))[0]
+    sd = O.randomize_bn(O.resnet_deconv_init(18, c["J"], c["ds"], c["seed"], head_std=c["head_std"]), c["seed"] + 1)
+    m = awr_b200.get_deconv_net(18, c["J"], c["ds"], precision="fp32")
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev).eval()
+    img, _ = O.synthetic_batch(c["B"], c["H"], c["J"], c["seed"] + 2)
+    with torch.no_grad():
+        pred = m(img.to(dev))
+        uvd = awr_b200.FeatureModule().offset2joint_softmax(pred, img.to(dev), c["ks"])
+    diff = (uvd.cpu() - c["eval_uvd"][0]).abs().max().item()
+    return {"config": "resnet_18-deconv + AWR head, 1x128x128 depth crop, 14 joints, batch 1, fp32 forward (eval-mode BN)",
+            "uvd_max_abs_diff": diff, "tolerance": 1e-3, "pass": diff < 1e-3,
+            "against": "unmodified reference on CPU, recorded in tests/golden/backbone_cases.pt[0] by tests/golden/make_golden.py"}
+
+
+def gpu_eager_steps(net, ds, ks, batch, dev, steps=10, autocast=False):
+    """The oracle's functional torch ops (cuDNN conv, eager elementwise, autograd) on the GPU: what `train.py` costs on this box without
+    our kernels.  Same step as cpu_train_steps (Adam through torch ops).  Reported for scale only."""
+    import torch
+    from oracle import awr_oracle as O
+    kind, n = net.split("_")
+    sd = O.resnet_deconv_init(int(n), J, ds, 1) if kind == "resnet" else O.hourglass_init(int(n), J, 1)
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    img, jt = O.synthetic_batch(batch, H, J, 0)
+    img, jt = img.to(dev), jt.to(dev)
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()
+             if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+
+    def one(it):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            _, lc, ld, _, _, grads, new_stats = O.loss_and_grads(sd, img, jt, net, ds, ks, 1.0, 1.0)
+        with torch.no_grad():
+            for k, g in grads.items():
+                if g is not None:
+                    O.adam_step(sd[k], g.float(), state[k][0], state[k][1], it + 1)
+            for k, v in new_stats.items():
+                sd[k] = v
+    for it in range(3):
+        one(it)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(steps):
+        one(3 + it)
+    e1.record()
+    torch.cuda.synchronize()
+    return batch * steps / (e0.elapsed_time(e1) * 1e-3)
 
 
 def run_reference(a):
@@ -369,6 +428,17 @@ def main():
         cpu = {"value": round(fps, 3), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{a.cpu_steps} full train steps (1 warm-up) at batch {a.batch}, fp32, oracle/awr_oracle.py on torch CPU ops"}
 
+    parity = eager = None
+    if rank == 0 and world == 1 and not a.no_parity and a.net == "resnet_18" and H == 128:
+        parity = parity_c1(dev)
+    if rank == 0 and world == 1 and a.gpu_eager_baseline:
+        eager = {"unit": UNIT, "what": "oracle's torch ops on this GPU (eager, cuDNN), same train step, device-resident batch"}
+        for key, ac in (("fp32", False), ("bf16_autocast", True)):
+            try:
+                eager[key] = round(gpu_eager_steps(a.net, ds, ks, a.batch, dev, autocast=ac), 1)
+            except Exception as e:          # a baseline leg must never cost the bench line
+                eager[key] = f"failed: {type(e).__name__}: {e}"[:200]
+
     if rank == 0:
         act_bytes = sum(op.y.t.numel() * op.y.t.element_size() for op in tr.plan.ops if hasattr(op, "y"))
         cfg = workload_config(a, world)
@@ -381,7 +451,9 @@ def main():
                         "ms_per_step": round(ms_e2e / a.steps, 4)},
                 "gpu_launches": tr.launches_per_step * a.steps, "launches_per_step": tr.launches_per_step,
                 "roofline": roof, "roofline_head": roof_head, "kernel_classes": classes, "cpu_baseline": cpu,
-                "loss": {"coord": lc, "dense": ld}}
+                "loss": {"coord": lc, "dense": ld}, "parity": parity}
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -17,9 +17,8 @@ namespace {
 constexpr float kSoftmaxScale = 30.0f;     // feature_tool.py:60
 constexpr float kDepthBg = 0.99f;          // feature_tool.py:35,57
 constexpr int kHeadThreads = 128;
-// A (frame, joint) pair is streamed by S CTAs (S = 1, 2 or 4; forward: one thread-block cluster whose online-softmax states are
-// combined through distributed shared memory; backward: independent CTAs).  At the headline size B*J = 448 pairs are only 3 CTAs
-// of 4 warps per SM: S = 2 doubles the loads in flight and evens out the 3-vs-4 CTA imbalance across the 148 SMs.
+// A (frame, joint) pair is streamed by S CTAs (S = 1 by default; 2 or 4 on request: forward = one thread-block cluster whose
+// online-softmax states are combined through distributed shared memory, backward = independent CTAs).  See head_split().
 
 struct Px4 { float v[4]; };
 
@@ -363,14 +362,13 @@ huber_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long 
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dx[i] = k * huber_grad(x[i] - y[i]);
 }
 
-// CTAs per (frame, joint) pair: enough CTAs for ~6 per SM while every thread keeps >= 4 pixel groups.  AWR_HEAD_SPLIT=1|2|4 overrides.
+// CTAs per (frame, joint) pair.  Measured on B200 (tools/bench_head.py, B=32 J=14 F=64, cold L2): forward 20.5 / 24.6 / 28.7 us and
+// backward 21.5 / 22.6 / 22.7 us for S = 1 / 2 / 4 -- the kernels are bound by instruction issue per pixel, not by CTA count, and the
+// cluster launch + two cluster barriers cost more than the finer granularity returns.  S = 1 unless AWR_HEAD_SPLIT=2|4 forces a split.
 int head_split(int B, int J, int F) {
-  static const int forced = [] { const char* e = getenv("AWR_HEAD_SPLIT"); const int v = e ? atoi(e) : 0; return (v == 1 || v == 2 || v == 4) ? v : 0; }();
-  if (forced) return forced;
-  const long long pairs = (long long)B * J, groups_per_thread = ((long long)F * F / 4) / kHeadThreads;
-  int S = 1;
-  while (S < 4 && pairs * S < 148 * 6 && groups_per_thread / (2 * S) >= 4) S *= 2;
-  return S;
+  static const int forced = [] { const char* e = getenv("AWR_HEAD_SPLIT"); const int v = e ? atoi(e) : 0; return (v == 2 || v == 4) ? v : 1; }();
+  (void)B; (void)J;
+  return ((F * F / 4) % forced == 0) ? forced : 1;
 }
 
 // forward launch: S-CTA clusters + programmatic dependent launch

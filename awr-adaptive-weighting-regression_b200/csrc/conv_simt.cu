@@ -339,33 +339,50 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __res
     const int hy = (int)(t % H);
     const int n = (int)(t / H);
     const int wx = w4 * 4;
-    float acc[4][8];
-#pragma unroll
-    for (int p4 = 0; p4 < 4; ++p4)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc[p4][q] = bias ? bias[cg * 8 + q] : 0.f;
     const float* xi = x + (long long)n * H * W;
+    // the whole K x (4+K-1) input patch first: three aligned 16-byte loads per row (columns wx-4 .. wx+7), rows / columns outside the
+    // image read as zero from clamped addresses -- all 3K loads are in flight before the first FMA
+    static_assert(K == 5, "patch loader is written for the 5x5 stem");
+    float xs[K][XS];
 #pragma unroll
     for (int r = 0; r < K; ++r) {
       const int hh = hy + r - PADK;
-      if (hh < 0 || hh >= H) continue;
-      float xs[XS];
+      const bool rok = (hh >= 0 && hh < H);
+      const float* row = xi + (long long)min(max(hh, 0), H - 1) * W;
+      const bool lok = rok && wx >= 4, rok2 = rok && wx + 4 < W;
+      const float4 l4 = __ldg(reinterpret_cast<const float4*>(row + (wx >= 4 ? wx - 4 : 0)));
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(row + wx));
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(row + (wx + 4 < W ? wx + 4 : wx)));
+      xs[r][0] = lok ? l4.z : 0.f; xs[r][1] = lok ? l4.w : 0.f;
+      xs[r][2] = rok ? m4.x : 0.f; xs[r][3] = rok ? m4.y : 0.f; xs[r][4] = rok ? m4.z : 0.f; xs[r][5] = rok ? m4.w : 0.f;
+      xs[r][6] = rok2 ? r4.x : 0.f; xs[r][7] = rok2 ? r4.y : 0.f;
+    }
+    // accumulators as channel pairs: one packed FFMA2 (fma.rn.f32x2, sm_100) = two IEEE FMAs, half the issue slots
+    float2 acc2[4][4];
 #pragma unroll
-      for (int c = 0; c < XS; ++c) {
-        const int ww = wx + c - PADK;
-        xs[c] = (ww >= 0 && ww < W) ? __ldg(xi + (long long)hh * W + ww) : 0.f;
-      }
+    for (int p4 = 0; p4 < 4; ++p4)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc2[p4][q] = bias ? make_float2(bias[cg * 8 + 2 * q], bias[cg * 8 + 2 * q + 1]) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
 #pragma unroll
       for (int s2_ = 0; s2_ < K; ++s2_) {
         const float4 wa = *reinterpret_cast<const float4*>(ws + (r * K + s2_) * Cout + cg * 8);
         const float4 wb = *reinterpret_cast<const float4*>(ws + (r * K + s2_) * Cout + cg * 8 + 4);
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        const float2 w2[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
 #pragma unroll
-        for (int p4 = 0; p4 < 4; ++p4)
+        for (int p4 = 0; p4 < 4; ++p4) {
+          const float2 x2 = make_float2(xs[r][p4 + s2_], xs[r][p4 + s2_]);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[p4][q] = fmaf(xs[p4 + s2_], wv[q], acc[p4][q]);
+          for (int q = 0; q < 4; ++q) acc2[p4][q] = __ffma2_rn(x2, w2[q], acc2[p4][q]);
+        }
       }
     }
+    float acc[4][8];
+#pragma unroll
+    for (int p4 = 0; p4 < 4; ++p4)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { acc[p4][2 * q] = acc2[p4][q].x; acc[p4][2 * q + 1] = acc2[p4][q].y; }
 #pragma unroll
     for (int p4 = 0; p4 < 4; ++p4) {
       Vec8<T>::store(y + ((((long long)n * H + hy) * W + wx + p4) * G + cg) * 8, acc[p4]);
@@ -433,7 +450,7 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, 
 int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, float* stats, int dtype, int N, int H, int W, int Cout, int k,
                   void* stream) {
   AWR_HOST_CHECK(x && w && y && N > 0 && Cout % 8 == 0 && k % 2 == 1 && k <= 7);
-  if (k == 5 && W % 4 == 0 && (256 % (Cout / 8)) == 0) {
+  if (k == 5 && W % 4 == 0 && (256 % (Cout / 8)) == 0 && (reinterpret_cast<unsigned long long>(x) & 15ull) == 0ull) {   // 16-byte patch loads
     const long long items4 = (long long)N * H * (W / 4) * (Cout / 8);
     long long blocks4 = (items4 + 255) / 256;
     if (blocks4 > 148 * 8) blocks4 = 148 * 8;

@@ -180,6 +180,33 @@ __device__ __forceinline__ void bn_coeffs(const BnSet& b, int c, int C, float in
   sh = b.beta[c] - mean * sc;
 }
 
+// 8 consecutive floats as two 16-byte loads (scalar fallback for pointers that are not 16-byte aligned)
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&v)[8]) {
+  if ((reinterpret_cast<unsigned long long>(p) & 15ull) == 0ull) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[k];
+  }
+}
+// scale / shift of channels c0..c0+7.  All eight vector loads are issued before the first rsqrt: with scalar bn_coeffs() calls the
+// compiler serialises load -> rsqrt per channel, i.e. up to 16 dependent L2 round trips (3-6 us) at the head of every BatchNorm launch.
+__device__ __forceinline__ void bn_coeffs8(const BnSet& b, int c0, int C, float inv_count, float eps, int training, float (&sc)[8], float (&sh)[8]) {
+  float m[8], v[8], g[8], be[8];
+  if (training) { load8f(b.sums + c0, m); load8f(b.sums + C + c0, v); }
+  else { load8f(b.running_mean + c0, m); load8f(b.running_var + c0, v); }
+  load8f(b.gamma + c0, g); load8f(b.beta + c0, be);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float mean = m[k], var = v[k];
+    if (training) { mean = m[k] * inv_count; var = fmaxf(v[k] * inv_count - mean * mean, 0.f); }
+    const float invstd = rsqrtf(var + eps);
+    sc[k] = g[k] * invstd;
+    sh[k] = be[k] - mean * sc[k];
+  }
+}
+
 __device__ __forceinline__ void bn_side_effects(const BnSet& b, int C, float count, float momentum, float eps, int training) {
   const float inv_count = 1.0f / count;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -196,30 +223,38 @@ __device__ __forceinline__ void bn_side_effects(const BnSet& b, int C, float cou
 }
 
 template <typename T, int U>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 2)
 bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSet rbn, int res_has_bn, T* __restrict__ out, long long M, int C,
               float count, float momentum, float eps, int training, int relu) {
   pdl_entry();
+  // the LAST CTA only performs the side effects (running statistics, saved mean/invstd): nothing else in this grid reads what it
+  // writes (training reads the batch sums, eval writes no statistics), so it runs beside the streaming CTAs instead of after them
+  if (blockIdx.x == gridDim.x - 1) {
+    bn_side_effects(bn, C, count, momentum, eps, training);
+    if (res_has_bn) bn_side_effects(rbn, C, count, momentum, eps, training);
+    return;
+  }
   const int G = C >> 3;
-  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  const long long items = M * G, stride = (long long)(gridDim.x - 1) * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   const int c0 = (int)(first % G) * 8;
-  const float inv_count = 1.0f / count;
-  float sc[8], sh[8], rsc[8], rsh[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float mean, invstd, var;
-    bn_coeffs(bn, c0 + k, C, inv_count, eps, training, sc[k], sh[k], mean, invstd, var);
-    if (res_has_bn) bn_coeffs(rbn, c0 + k, C, inv_count, eps, training, rsc[k], rsh[k], mean, invstd, var);
-  }
-  // U items per thread and iteration; every load of the batch is issued before the first use (bytes in flight, see ew_grid)
-  for (long long i0 = first; i0 < items; i0 += U * stride) {
-    Raw8<T> ry[U], rr[U];
+  // U items per thread and iteration; every load of a batch is issued before its first use, and the first batch is issued BEFORE the
+  // per-channel coefficient loads so that the two dependent DRAM/L2 round trips of a small tensor overlap
+  Raw8<T> ry[U], rr[U];
+  auto load_batch = [&](long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
       if (i < items) { ry[u].load(y + i * 8); if (res) rr[u].load(res + i * 8); }
     }
+  };
+  long long i0 = first;
+  if (i0 < items) load_batch(i0);
+  const float inv_count = 1.0f / count;
+  float sc[8], sh[8], rsc[8], rsh[8];
+  bn_coeffs8(bn, c0, C, inv_count, eps, training, sc, sh);
+  if (res_has_bn) bn_coeffs8(rbn, c0, C, inv_count, eps, training, rsc, rsh);
+  while (i0 < items) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
@@ -244,11 +279,8 @@ bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSe
       }
       Vec8<T>::store(out + i * 8, v);
     }
-  }
-  if (blockIdx.x == gridDim.x - 1) {      // side effects after this block's own reads of the running statistics
-    __syncthreads();
-    bn_side_effects(bn, C, count, momentum, eps, training);
-    if (res_has_bn) bn_side_effects(rbn, C, count, momentum, eps, training);
+    i0 += U * stride;
+    if (i0 < items) load_batch(i0);
   }
 }
 
@@ -267,8 +299,7 @@ bn_relu_maxpool_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ ou
   const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
   float sc[8], sh[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { float mean, invstd, var; bn_coeffs(bn, c0 + q, C, 1.0f / count, eps, training, sc[q], sh[q], mean, invstd, var); }
+  bn_coeffs8(bn, c0, C, 1.0f / count, eps, training, sc, sh);
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
     long long t = i / G;
     const int wo = (int)(t % Wo); t /= Wo;
@@ -316,8 +347,7 @@ bn_relu_maxpool3_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ o
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
   const float inv_count = 1.0f / count;
   float sc[8], sh[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { float mean, invstd, var; bn_coeffs(bn, c0 + q, C, inv_count, eps, training, sc[q], sh[q], mean, invstd, var); }
+  bn_coeffs8(bn, c0, C, inv_count, eps, training, sc, sh);
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
     long long t = i / G;
     const int wo = (int)(t % Wo); t /= Wo;
@@ -530,7 +560,7 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
 // BN backward, pass 1: dz = dout * (act_out > 0 if relu);  dsums[0:C] += sum dz ; dsums[C:2C] += sum dz * yhat
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int U>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 2)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
                      const float* __restrict__ mean_invstd, long long M, int C, float* __restrict__ dsums,
                      const float* __restrict__ mask_gamma, const float* __restrict__ mask_beta) {
@@ -540,6 +570,20 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   const int c0 = (int)(first % G) * 8;
+  const bool use_act = !mask_gamma && act_out;
+  Raw8<T> rg[U], ry[U], ra[U];
+  auto load_batch = [&](long long i0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < items) {
+        rg[u].load(dout + i * 8); ry[u].load(y + i * 8);
+        if (use_act) ra[u].load(act_out + i * 8);
+      }
+    }
+  };
+  long long i0 = first;
+  if (i0 < items) load_batch(i0);          // in flight while the per-channel constants are fetched
   float mean[8], istd[8], msc[8], msh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -547,16 +591,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
     if (mask_gamma) { msc[k] = mask_gamma[c0 + k] * istd[k]; msh[k] = mask_beta[c0 + k] - mean[k] * msc[k]; }
   }
   float acc[2][8] = {};
-  for (long long i0 = first; i0 < items; i0 += U * stride) {
-    Raw8<T> rg[U], ry[U], ra[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < items) {
-        rg[u].load(dout + i * 8); ry[u].load(y + i * 8);
-        if (!mask_gamma && act_out) ra[u].load(act_out + i * 8);
-      }
-    }
+  while (i0 < items) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i0 + u * stride >= items) break;
@@ -574,6 +609,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
 #pragma unroll
       for (int k = 0; k < 8; ++k) { acc[0][k] += g[k]; acc[1][k] += g[k] * (yy[k] - mean[k]) * istd[k]; }
     }
+    i0 += U * stride;
+    if (i0 < items) load_batch(i0);
   }
   block_channel_reduce<2>(acc, G, C, dsums, smem);
 }
@@ -582,27 +619,28 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
 // block 0 also writes dgamma / dbeta.  dy may alias dy_addend and dres may alias dres_addend (read-modify-write of thread-private
 // items: every load of a batch precedes its stores).
 template <typename T, int U>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
                     const float* __restrict__ mean_invstd, const float* __restrict__ dsums, const float* __restrict__ gamma,
                     T* dy, const T* dy_addend, T* dres, const T* dres_addend, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, long long M, int C, int accumulate_param_grads, const float* __restrict__ mask_beta) {
   pdl_entry();
+  if (blockIdx.x == gridDim.x - 1) {       // dedicated CTA: dgamma / dbeta from the reduced sums, beside the streaming CTAs
+    if (dgamma) {
+      for (int c = threadIdx.x; c < C; c += kEwThreads) {
+        if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
+        else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
+      }
+    }
+    return;
+  }
   const int G = C >> 3;
-  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  const long long items = M * G, stride = (long long)(gridDim.x - 1) * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   const int c0 = (int)(first % G) * 8;
-  const float invM = 1.0f / (float)M;
-  float mean[8], istd[8], k1[8], k2[8], gs[8], msh[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k];
-    k1[k] = dsums[c0 + k] * invM; k2[k] = dsums[C + c0 + k] * invM; gs[k] = gamma[c0 + k] * istd[k];
-    msh[k] = mask_beta ? mask_beta[c0 + k] - mean[k] * gs[k] : 0.f;
-  }
   const bool use_act = !mask_beta && act_out, add_res = dres && dres_addend;
-  for (long long i0 = first; i0 < items; i0 += U * stride) {
-    Raw8<T> rg[U], ry[U], ra[U], rb[U], rc[U];
+  Raw8<T> rg[U], ry[U], ra[U], rb[U], rc[U];
+  auto load_batch = [&](long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
@@ -613,6 +651,18 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
         if (dy_addend) rc[u].load(dy_addend + i * 8);
       }
     }
+  };
+  long long i0 = first;
+  if (i0 < items) load_batch(i0);          // in flight while the per-channel constants are fetched
+  const float invM = 1.0f / (float)M;
+  float mean[8], istd[8], k1[8], k2[8], gs[8], msh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k];
+    k1[k] = dsums[c0 + k] * invM; k2[k] = dsums[C + c0 + k] * invM; gs[k] = gamma[c0 + k] * istd[k];
+    msh[k] = mask_beta ? mask_beta[c0 + k] - mean[k] * gs[k] : 0.f;
+  }
+  while (i0 < items) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
@@ -648,12 +698,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
       }
       Vec8<T>::store(dy + i * 8, o);
     }
-  }
-  if (blockIdx.x == 0 && dgamma) {
-    for (int c = threadIdx.x; c < C; c += kEwThreads) {
-      if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
-      else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
-    }
+    i0 += U * stride;
+    if (i0 < items) load_batch(i0);
   }
 }
 
@@ -981,7 +1027,7 @@ int awr_bn_act(const void* y, const float* sums, const float* gamma, const float
   AWR_HOST_CHECK(!res_has_bn || (res && res_beta && (training ? (res_sums != nullptr) : (res_running_mean && res_running_var))));
   BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
   BnSet b{res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
-  DISPATCH_TU(dtype, launch_pdl(bn_act_kernel<T, U>, dim3(ew_grid(M * (C / 8), U)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a,
+  DISPATCH_TU(dtype, launch_pdl(bn_act_kernel<T, U>, dim3(ew_grid(M * (C / 8), U) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a,
                                 (const T*)res, b, res_has_bn, (T*)out, M, C, (float)M, momentum, eps, training, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1048,7 +1094,7 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
                      float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && gamma && dy && M > 0 && chan_ok(C));
   // up to five tensors are read per item here: two items per batch keep the kernel at 128 registers = 2 CTAs per SM
-  DISPATCH_TU(dtype, launch_pdl(bn_bwd_apply_kernel<T, (U > 2 ? 2 : U)>, dim3(ew_grid(M * (C / 8), (U > 2 ? 2 : U))), dim3(kEwThreads), 0, (cudaStream_t)stream,
+  DISPATCH_TU(dtype, launch_pdl(bn_bwd_apply_kernel<T, (U > 2 ? 2 : U)>, dim3(ew_grid(M * (C / 8), (U > 2 ? 2 : U)) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream,
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
                         (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads, mask_beta));
   AWR_LAUNCH_CHECK();

@@ -5,6 +5,7 @@
 // K=25).  The bf16 throughput path is conv_tc.cu.  Replaces nn.Conv2d / nn.ConvTranspose2d forward + autograd
 // (model/resnet_deconv.py:31-32,78-86,141-142,182-188; model/hourglass.py:10) for this mode.
 #include "common.cuh"
+#include <cstdlib>
 #include "awr_b200.h"
 
 namespace {
@@ -318,6 +319,87 @@ __global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __re
   }
 }
 
+// Channel-pair variant of the kernel above (Cout = 64): a thread owns TWO adjacent output channels (one 4-byte bf16x2 / 8-byte fp32x2
+// load per pixel, 128 contiguous bytes per warp) and a warp is one of 8 groups walking the band's 8-pixel row segments.  All K*K tap
+// accumulators are channel pairs updated with packed FFMA2 (two IEEE FMAs per instruction) and the x row comes from shared memory
+// as three 16-byte loads: ~300 instructions per segment and channel pair instead of 2 x 280.
+template <typename T> struct Pair2;
+template <> struct Pair2<float> { static __device__ __forceinline__ float2 load(const float* p) { return *reinterpret_cast<const float2*>(p); } };
+template <> struct Pair2<bf16> {
+  static __device__ __forceinline__ float2 load(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+};
+template <typename T, int K>
+__global__ void __launch_bounds__(256) stem_wgrad_pair_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
+                                                              float* __restrict__ dbias, int N, int H, int W) {
+  pdl_entry();
+  constexpr int RB = 8, CO = 64, PADK = K / 2, XS = 12, KK = K * K, HALF = (KK + 2) / 2;     // 26 values (taps + bias) in two rounds of 13
+  static_assert(K == 5, "row loader is written for the 5x5 stem");
+  extern __shared__ __align__(16) float sm[];
+  const int pitch = ((W + K - 1) + 3) & ~3;
+  float* xt = sm;                                   // [(RB+K-1)][pitch]
+  float* red = sm + (RB + K - 1) * pitch;           // [8 groups][HALF][CO]
+  const int n = blockIdx.x / (H / RB), h0 = (blockIdx.x % (H / RB)) * RB;
+  const int cp = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const float* xi = x + (size_t)n * H * W;
+  for (int i = threadIdx.x; i < (RB + K - 1) * pitch; i += 256) {
+    const int rr = i / pitch, cc = i - rr * pitch;
+    const int hh = h0 + rr - PADK, ww = cc - PADK;
+    xt[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W && cc < W + K - 1) ? __ldg(xi + (size_t)hh * W + ww) : 0.f;
+  }
+  __syncthreads();
+  float2 acc[KK];
+#pragma unroll
+  for (int t = 0; t < KK; ++t) acc[t] = make_float2(0.f, 0.f);
+  float2 bsum = make_float2(0.f, 0.f);
+  const int octs_per_row = W / 8, octs = RB * octs_per_row;
+  for (int o = grp; o < octs; o += 8) {
+    const int rr = o / octs_per_row, c0 = (o - rr * octs_per_row) * 8;
+    const T* dyp = dy + (((size_t)n * H + h0 + rr) * W + c0) * CO + 2 * cp;
+    float2 g[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = Pair2<T>::load(dyp + (size_t)i * CO);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { bsum.x += g[i].x; bsum.y += g[i].y; }
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const float4* xr = reinterpret_cast<const float4*>(xt + (rr + r) * pitch + c0);      // 16-byte aligned: pitch % 4 == 0, c0 % 8 == 0
+      const float4 xa = xr[0], xb = xr[1], xc = xr[2];
+      const float xs[XS] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+      for (int s2 = 0; s2 < K; ++s2) {
+        float2 a = acc[r * K + s2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a = __ffma2_rn(make_float2(xs[i + s2], xs[i + s2]), g[i], a);
+        acc[r * K + s2] = a;
+      }
+    }
+  }
+  // cross-group reduction through shared memory in two rounds of HALF values, then one atomicAdd per (tap, channel) per block
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+#pragma unroll
+    for (int tt = 0; tt < HALF; ++tt) {
+      const int t = half * HALF + tt;
+      if (t <= KK) {
+        const float2 v = (t < KK) ? acc[t < KK ? t : 0] : bsum;
+        red[(grp * HALF + tt) * CO + 2 * cp] = v.x;
+        red[(grp * HALF + tt) * CO + 2 * cp + 1] = v.y;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < HALF * CO; e += 256) {
+      const int tt = e / CO, co = e - tt * CO, t = half * HALF + tt;
+      if (t > KK) continue;
+      float v = 0.f;
+#pragma unroll
+      for (int g2 = 0; g2 < 8; ++g2) v += red[(g2 * HALF + tt) * CO + co];
+      if (t < KK) atomicAdd(dW + t * CO + co, v);
+      else if (dbias) atomicAdd(dbias + co, v);
+    }
+  }
+}
+
 // Register-tiled stem convolution: thread = 4 consecutive pixels of a row x 8 output channels (32 accumulators); the 5 x 8 input
 // patch is read once per thread and every weight vector fetched from shared memory feeds 4 pixels.  Optionally accumulates the
 // BatchNorm batch statistics (per-channel sum / sum of squares of the stored values) so no separate reduction pass is needed.
@@ -480,6 +562,13 @@ int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int 
   AWR_HOST_CHECK((k * k + (256 / Cout) - 1) / (256 / Cout) <= 8);
   if (k == 5 && Cout == 64 && H % 8 == 0 && W % 8 == 0 && W <= 256) {
     const int pitch = ((W + 4) + 3) & ~3;
+    static const bool old_kernel = [] { const char* e = getenv("AWR_STEM_WGRAD"); return e && e[0] == 'o'; }();       // AWR_STEM_WGRAD=old
+    if (!old_kernel) {
+      const size_t smem2 = ((size_t)12 * pitch + 8 * 13 * 64) * sizeof(float);
+      DISPATCH_T(dtype, launch_pdl(stem_wgrad_pair_kernel<T, 5>, dim3(N * (H / 8)), dim3(256), smem2, (cudaStream_t)stream, x, (const T*)dy, dW, dbias, N, H, W));
+      AWR_LAUNCH_CHECK();
+      return AWR_OK;
+    }
     const size_t smem = ((size_t)12 * pitch + 4 * 26 * 64) * sizeof(float);
     DISPATCH_T(dtype, launch_pdl(stem_wgrad_tiled_kernel<T, 5>, dim3(N * (H / 8)), dim3(256), smem, (cudaStream_t)stream, x, (const T*)dy, dW, dbias, N, H, W));
     AWR_LAUNCH_CHECK();

@@ -365,6 +365,38 @@ bn_relu_maxpool3_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ o
         if (hi == hc && wi == wc) valid |= 1u << (r * 3 + c);
       }
     }
+    if constexpr (sizeof(T) == 2) {
+      // bf16 storage: the stored activation is >= 0 with 16 spare low bits, so (bits << 16 | 15 - tap) orders candidates by value and,
+      // among equal values, by scan order -- one unsigned max per (tap, channel) replaces compare + two selects
+      unsigned key[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) key[q] = 0u;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        if (!((valid >> tap) & 1u)) continue;
+        float v[8];
+        raw[tap].unpack(v);
+        const unsigned tag = 15u - (unsigned)tap;
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) {
+          const float a0 = fmaxf(v[2 * q2] * sc[2 * q2] + sh[2 * q2], 0.f), a1 = fmaxf(v[2 * q2 + 1] * sc[2 * q2 + 1] + sh[2 * q2 + 1], 0.f);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+          const unsigned pr = *reinterpret_cast<const unsigned*>(&h) & 0x7fff7fffu;      // -0.0 -> +0.0
+          key[2 * q2] = max(key[2 * q2], (pr << 16) | tag);
+          key[2 * q2 + 1] = max(key[2 * q2 + 1], (pr & 0xffff0000u) | tag);
+        }
+      }
+      uint4 o;
+      o.x = (key[0] >> 16) | (key[1] & 0xffff0000u); o.y = (key[2] >> 16) | (key[3] & 0xffff0000u);
+      o.z = (key[4] >> 16) | (key[5] & 0xffff0000u); o.w = (key[6] >> 16) | (key[7] & 0xffff0000u);
+      *reinterpret_cast<uint4*>(out + i * 8) = o;
+      if (idx) {
+        uint2 pk;
+        pk.x = (15u - (key[0] & 15u)) | ((15u - (key[1] & 15u)) << 8) | ((15u - (key[2] & 15u)) << 16) | ((15u - (key[3] & 15u)) << 24);
+        pk.y = (15u - (key[4] & 15u)) | ((15u - (key[5] & 15u)) << 8) | ((15u - (key[6] & 15u)) << 16) | ((15u - (key[7] & 15u)) << 24);
+        *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+      }
+    } else {
     float best[8];
     unsigned char bi[8];
 #pragma unroll
@@ -386,6 +418,7 @@ bn_relu_maxpool3_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ o
       pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((unsigned)bi[3] << 24);
       pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((unsigned)bi[7] << 24);
       *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
     }
   }
   if (blockIdx.x == gridDim.x - 1) { __syncthreads(); bn_side_effects(bn, C, count, momentum, eps, training); }

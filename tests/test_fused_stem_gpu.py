@@ -66,3 +66,50 @@ def test_bn_relu_maxpool_fwd_and_bwd(k, s, p):
     scale = yr.grad.abs().max().item()
     assert (dy.permute(0, 3, 1, 2) - yr.grad).abs().max().item() < 1e-4 * scale + 1e-6
     assert torch.allclose(dg, gr.grad, rtol=1e-4, atol=1e-4) and torch.allclose(db, br.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_bn_relu_maxpool3_fwd_bf16_value_and_argmax():
+    """bf16 storage path of the 3x3/2/1 kernel (packed value|tap keys): pooled values match torch on the bf16-rounded activation,
+    every arg-max byte points at a tap holding the pooled value, and ties (all-zero windows) resolve to the first valid tap as ATen does."""
+    from awr_b200 import _lib as L
+    N, C, H, k, s, p = 2, 64, 32, 3, 2, 1
+    g = torch.Generator().manual_seed(5)
+    y = (torch.randn(N, C, H, H, generator=g) - 0.4).cuda().bfloat16()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.3).cuda()
+    yf = y.float()
+    yn = _nhwc(y)
+    ynf = yn.float()
+    sums = torch.cat([ynf.sum(dim=(0, 1, 2)), (ynf * ynf).sum(dim=(0, 1, 2))]).contiguous()
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.long, device="cuda")
+    mi = torch.empty(2 * C, device="cuda")
+    Ho = (H + 2 * p - k) // s + 1
+    out = torch.empty(N, Ho, Ho, C, device="cuda", dtype=torch.bfloat16)
+    idx = torch.empty(N, Ho, Ho, C, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().awr_bn_relu_maxpool_fwd(yn.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                            nbt.data_ptr(), mi.data_ptr(), out.data_ptr(), idx.data_ptr(), L.BF16, N, H, H, C, k, s, p, 0.1, 1e-5, 1,
+                                            L.stream()), "fwd")
+    torch.cuda.synchronize()
+    cnt = N * H * H
+    mean = sums[:C] / cnt
+    var = (sums[C:] / cnt - mean * mean).clamp_min(0)
+    sc = gamma * torch.rsqrt(var + 1e-5)
+    sh = beta - mean * sc
+    act = F.relu(yf * sc.view(1, C, 1, 1) + sh.view(1, C, 1, 1)).bfloat16().float()          # what the unfused path would have stored
+    ref = F.max_pool2d(act, k, s, p)
+    o = out.float().permute(0, 3, 1, 2)
+    assert (o - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()                      # one bf16 ulp of slack for sc/sh rounding
+    # arg-max consistency: the tap each byte names holds the pooled value
+    tap = idx.long().permute(0, 3, 1, 2)
+    ho = torch.arange(Ho, device="cuda").view(1, 1, Ho, 1)
+    wo = torch.arange(Ho, device="cuda").view(1, 1, 1, Ho)
+    hi, wi = ho * s - p + tap // k, wo * s - p + tap % k
+    assert (hi >= 0).all() and (hi < H).all() and (wi >= 0).all() and (wi < H).all()
+    picked = act[torch.arange(N, device="cuda").view(N, 1, 1, 1), torch.arange(C, device="cuda").view(1, C, 1, 1), hi, wi]
+    assert (picked - o).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    # ties: an all-zero window resolves to its first valid tap (row-major scan)
+    zero = (o == 0)
+    first_r = (p - ho * s).clamp_min(0)
+    first_c = (p - wo * s).clamp_min(0)
+    first = (first_r * k + first_c).expand_as(tap)
+    assert zero.any() and (tap[zero] == first[zero]).all()

@@ -412,11 +412,17 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __res
   __syncthreads();
   constexpr int PADK = K / 2, XS = 4 + K - 1;
   const int G = Cout >> 3, W4 = W >> 2;
-  const long long items = (long long)N * H * W4 * G, stride = (long long)gridDim.x * blockDim.x;
-  const int cg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % G);
+  // Cout == 64 (G == 8 == warps per CTA): a WARP owns one channel octet and its lanes 32 consecutive pixel quads.  The weight
+  // vectors are then warp-uniform (broadcast LDS, no bank conflicts -- with the octet varying across lanes the two 16-byte weight loads
+  // per tap were 2-way conflicted and their shared-memory bandwidth, not the FMA pipe, bounded the kernel) and the x loads coalesce.
+  const bool wcg = (G == 8 && blockDim.x == 256);
+  const int lane = threadIdx.x & 31;
+  const int cg = wcg ? (int)(threadIdx.x >> 5) : (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) % G);
+  const long long items = (long long)N * H * W4 * (wcg ? 1 : G);
+  const long long stride = wcg ? (long long)gridDim.x * 32 : (long long)gridDim.x * blockDim.x;
   float s1[8] = {}, s2[8] = {};
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
-    long long t = i / G;
+  for (long long i = wcg ? (long long)blockIdx.x * 32 + lane : (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+    long long t = wcg ? i : i / G;
     const int w4 = (int)(t % W4); t /= W4;
     const int hy = (int)(t % H);
     const int n = (int)(t / H);
@@ -474,7 +480,15 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __res
       }
     }
   }
-  if (stats) {
+  if (stats && wcg) {
+    // the warp's 32 lanes share the channel octet: shuffle-reduce, one atomic per channel per warp
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { s1[q] = warp_sum(s1[q]); s2[q] = warp_sum(s2[q]); }
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { atomicAdd(stats + cg * 8 + q, s1[q]); atomicAdd(stats + Cout + cg * 8 + q, s2[q]); }
+    }
+  } else if (stats) {
     // threads with equal (threadIdx % G) share a channel octet: reduce over them in shared memory, one atomic per channel per block
     __syncthreads();
     float* red = ws;

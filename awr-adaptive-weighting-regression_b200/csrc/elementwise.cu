@@ -736,6 +736,142 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// BN backward in ONE launch for tensors whose operands fit in the shared memory of one CTA per SM (layer2-4 and deconv1 of
+// ResNet18 at 32 frames: 2-8 MB): every CTA pulls its contiguous slice of dout / y (/ the activation) into shared memory with 1-D
+// bulk TMA copies (cp.async.bulk ... mbarrier::complete_tx) -- the whole tensor is in flight at once, one DRAM/L2 round trip instead
+// of the two-to-four register-staged rounds of the two-pass kernels -- reduces sum(dz), sum(dz*yhat) from shared memory, meets the
+// other CTAs at a grid-wide barrier (all CTAs are co-resident by construction: grid <= SMs x occupancy), and then writes dy (and the
+// residual gradient) from the SAME shared-memory copy.  dout and y are read from global memory once instead of twice and the second
+// launch with its dependent prologue disappears.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(dst_smem)), "l"(src),
+               "r"(bytes), "r"(smem_addr_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads, 1)
+bn_bwd_fused_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y, const float* __restrict__ mean_invstd,
+                    const float* __restrict__ gamma, const float* __restrict__ mask_beta, float* dsums, unsigned* barrier, T* dy,
+                    const T* dy_addend, T* dres, const T* dres_addend, float* __restrict__ dgamma, float* __restrict__ dbeta, long long items,
+                    int C, float invM, int per, int accumulate_param_grads) {
+  extern __shared__ __align__(128) unsigned char fsm[];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(fsm);
+  float* red = reinterpret_cast<float*>(fsm + 128);                                       // kEwThreads * 8 floats
+  constexpr int IB = 8 * (int)sizeof(T);                                                  // bytes per 8-channel item
+  unsigned char* buf_g = fsm + 128 + kEwThreads * 8 * sizeof(float);
+  unsigned char* buf_y = buf_g + (size_t)per * IB;
+  unsigned char* buf_a = buf_y + (size_t)per * IB;
+  const bool use_act = !mask_beta && act_out;
+  const long long lo = (long long)blockIdx.x * per;
+  const int n_local = (int)max(0ll, min((long long)per, items - lo));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();                                   // the previous kernel's dout is visible from here on
+  if (threadIdx.x == 0 && n_local > 0) {
+    const unsigned bytes = (unsigned)n_local * IB, total = bytes * (use_act ? 3u : 2u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(total) : "memory");
+    for (unsigned off = 0; off < bytes; off += 16384u) {
+      const unsigned sz = min(16384u, bytes - off);
+      bulk_g2s(buf_g + off, reinterpret_cast<const unsigned char*>(dout) + (size_t)lo * IB + off, sz, bar);
+      bulk_g2s(buf_y + off, reinterpret_cast<const unsigned char*>(y) + (size_t)lo * IB + off, sz, bar);
+      if (use_act) bulk_g2s(buf_a + off, reinterpret_cast<const unsigned char*>(act_out) + (size_t)lo * IB + off, sz, bar);
+    }
+  }
+  // per-channel constants while the copies fly (lo is a multiple of 256 and 256 % G == 0: the octet of a thread never changes)
+  const int G = C >> 3;
+  const int c0 = (int)(threadIdx.x % G) * 8;
+  float mean[8], istd[8], gs[8], msh[8];
+  load8f(mean_invstd + c0, mean); load8f(mean_invstd + C + c0, istd); load8f(gamma + c0, gs);
+  if (mask_beta) load8f(mask_beta + c0, msh);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { gs[k] *= istd[k]; msh[k] = mask_beta ? msh[k] - mean[k] * gs[k] : 0.f; }
+  if (n_local > 0) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tFWAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra FDONE;\n\tbra FWAIT;\n\tFDONE:\n\t}" ::"r"(
+            smem_addr_u32(bar)),
+        "r"(0)
+        : "memory");
+  }
+  // pass 1 (shared memory only): dz = dout * mask, written back over dout; per-channel sums
+  float acc[2][8] = {};
+  for (int k = threadIdx.x; k < n_local; k += kEwThreads) {
+    float g[8], yy[8];
+    Vec8<T>::load(reinterpret_cast<const T*>(buf_g) + (size_t)k * 8, g);
+    Vec8<T>::load(reinterpret_cast<const T*>(buf_y) + (size_t)k * 8, yy);
+    if (mask_beta) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] = (from_store<T>(fmaxf(yy[q] * gs[q] + msh[q], 0.f)) > 0.f) ? g[q] : 0.f;
+      Vec8<T>::store(reinterpret_cast<T*>(buf_g) + (size_t)k * 8, g);
+    } else if (use_act) {
+      float a[8];
+      Vec8<T>::load(reinterpret_cast<const T*>(buf_a) + (size_t)k * 8, a);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] = (a[q] > 0.f) ? g[q] : 0.f;
+      Vec8<T>::store(reinterpret_cast<T*>(buf_g) + (size_t)k * 8, g);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { acc[0][q] += g[q]; acc[1][q] += g[q] * (yy[q] - mean[q]) * istd[q]; }
+  }
+  block_channel_reduce<2>(acc, G, C, dsums, red);
+  // grid-wide barrier (counter lives in the per-step zeroed arena)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(barrier, 1u);
+    while (ld_acquire_gpu(barrier) < gridDim.x) { __nanosleep(32); }
+  }
+  __syncthreads();
+  pdl_trigger();
+  float k1[8], k2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { k1[q] = __ldcg(dsums + c0 + q) * invM; k2[q] = __ldcg(dsums + C + c0 + q) * invM; }
+  // pass 2: dy / dres from the shared-memory copy
+  for (int k = threadIdx.x; k < n_local; k += kEwThreads) {
+    const long long i = lo + k;
+    float g[8], yy[8];
+    Vec8<T>::load(reinterpret_cast<const T*>(buf_g) + (size_t)k * 8, g);
+    Vec8<T>::load(reinterpret_cast<const T*>(buf_y) + (size_t)k * 8, yy);
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = gs[q] * (g[q] - k1[q] - (yy[q] - mean[q]) * istd[q] * k2[q]);
+    if (dres) {
+      if (dres_addend) {
+        float b[8];
+        Vec8<T>::load(dres_addend + i * 8, b);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] += b[q];
+      }
+      Vec8<T>::store(dres + i * 8, g);
+    }
+    if (dy_addend) {
+      float b[8];
+      Vec8<T>::load(dy_addend + i * 8, b);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] += b[q];
+    }
+    Vec8<T>::store(dy + i * 8, o);
+  }
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += kEwThreads) {
+      const float sg = __ldcg(dsums + C + c), sb = __ldcg(dsums + c);
+      if (accumulate_param_grads) { dgamma[c] += sg; dbeta[c] += sb; }
+      else { dgamma[c] = sg; dbeta[c] = sb; }
+    }
+  }
+}
+
 // relu backward / plain masked copy: dx = dout * (act_out > 0)  (+ add into existing dx when accumulate)
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
@@ -1130,6 +1266,54 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
   DISPATCH_TU(dtype, launch_pdl(bn_bwd_apply_kernel<T, (U > 2 ? 2 : U)>, dim3(ew_grid(M * (C / 8), (U > 2 ? 2 : U)) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream,
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
                         (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads, mask_beta));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+// geometry of the single-launch BN backward: grid (co-resident CTAs), items per CTA (multiple of 256), dynamic shared memory
+static bool bn_bwd_fused_geom(long long M, int C, int dtype, int with_act, int* grid, int* per, size_t* smem) {
+  if (!chan_ok(C) || M <= 0 || (dtype != AWR_DTYPE_F32 && dtype != AWR_DTYPE_BF16)) return false;
+  static const bool off = [] { const char* e = getenv("AWR_BN_FUSED"); return e && e[0] == '0'; }();       // AWR_BN_FUSED=0: two-pass kernels only
+  if (off) return false;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 1; }
+  const long long items = M * (C / 8);
+  long long g = (items + kEwThreads - 1) / kEwThreads;
+  if (g > sms) g = sms;
+  long long p = (items + g - 1) / g;
+  p = (p + kEwThreads - 1) / kEwThreads * kEwThreads;
+  g = (items + p - 1) / p;
+  const size_t ib = (dtype == AWR_DTYPE_F32) ? 32 : 16;
+  const size_t need = 128 + (size_t)kEwThreads * 8 * sizeof(float) + (size_t)(with_act ? 3 : 2) * (size_t)p * ib;
+  if (need > 200 * 1024) return false;
+  *grid = (int)g; *per = (int)p; *smem = need;
+  return true;
+}
+
+/* 1 when awr_bn_bwd_fused can take this tensor (operands fit in one CTA per SM), else 0: the caller then uses reduce + apply. */
+int awr_bn_bwd_fused_ok(long long M, int C, int dtype, int with_act) {
+  int g, p; size_t sm;
+  return bn_bwd_fused_geom(M, C, dtype, with_act, &g, &p, &sm) ? 1 : 0;
+}
+
+int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* gamma, const float* mask_beta,
+                     float* dsums, unsigned* barrier, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
+                     float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
+  AWR_HOST_CHECK(dout && y && mean_invstd && gamma && dsums && barrier && dy && M > 0 && chan_ok(C));
+  int grid, per; size_t smem;
+  const int with_act = (!mask_beta && act_out) ? 1 : 0;
+  if (!bn_bwd_fused_geom(M, C, dtype, with_act, &grid, &per, &smem)) return AWR_ERR_UNSUPPORTED;
+  static bool attr_set[2] = {false, false};
+  const int ti = (dtype == AWR_DTYPE_F32) ? 0 : 1;
+  if (!attr_set[ti]) {
+    cudaError_t e = (ti == 0) ? cudaFuncSetAttribute(bn_bwd_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+                              : cudaFuncSetAttribute(bn_bwd_fused_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[ti] = true;
+  }
+  DISPATCH_T(dtype, launch_pdl(bn_bwd_fused_kernel<T>, dim3(grid), dim3(kEwThreads), smem, (cudaStream_t)stream, (const T*)dout, (const T*)act_out,
+                               (const T*)y, mean_invstd, gamma, mask_beta, dsums, barrier, (T*)dy, (const T*)dy_addend, (T*)dres,
+                               (const T*)dres_addend, dgamma, dbeta, M * (long long)(C / 8), C, 1.0f / (float)M, per, accumulate_param_grads));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

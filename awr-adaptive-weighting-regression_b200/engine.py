@@ -625,7 +625,6 @@ class _BNAct(_Op):
         mg, mb = (pl.P(p + ".weight"), pl.P(p + ".bias")) if remask else (None, None)
         if remask:
             act = None
-        pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, y.t, self.bn.mi, mg, mb, pl.dt, y.M, y.C, self.bn.dsums, detail=self.detail)
         dy = y.grad()
         dy_add = dy if y.gw else None
         dres = dres_add = None
@@ -633,15 +632,26 @@ class _BNAct(_Op):
             dres = self.res.grad()
             dres_add = dres if self.res.gw else None
             self.res.gw = True
-        pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, y.t, self.bn.mi, self.bn.dsums, pl.P(p + ".weight"), dy, dy_add, dres, dres_add,
-                pl.G(p + ".weight"), pl.G(p + ".bias"), mb, pl.dt, y.M, y.C, 1, detail=self.detail)
+        # small tensors (operands fit in one CTA per SM): ONE launch -- bulk-TMA staging in shared memory, grid barrier, dy from the same copy
+        if pl.lib.awr_bn_bwd_fused_ok(y.M, y.C, pl.dt, int(act is not None)):
+            pl.call(pl.bwd, "awr_bn_bwd_fused", dout, act, y.t, self.bn.mi, pl.P(p + ".weight"), mb, self.bn.dsums, pl.arena(1), dy, dy_add,
+                    dres, dres_add, pl.G(p + ".weight"), pl.G(p + ".bias"), pl.dt, y.M, y.C, 1, tag="awr_bn_bwd_fused", detail=self.detail)
+        else:
+            pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, y.t, self.bn.mi, mg, mb, pl.dt, y.M, y.C, self.bn.dsums, detail=self.detail)
+            pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, y.t, self.bn.mi, self.bn.dsums, pl.P(p + ".weight"), dy, dy_add, dres, dres_add,
+                    pl.G(p + ".weight"), pl.G(p + ".bias"), mb, pl.dt, y.M, y.C, 1, detail=self.detail)
         y.gw = True
         if self.res_y is not None:
             ry, rp = self.res_y, self.res_prefix
-            pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, ry.t, self.bn_res.mi, None, None, pl.dt, ry.M, ry.C, self.bn_res.dsums)
             dry = ry.grad()
-            pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, ry.t, self.bn_res.mi, self.bn_res.dsums, pl.P(rp + ".weight"), dry,
-                    dry if ry.gw else None, None, None, pl.G(rp + ".weight"), pl.G(rp + ".bias"), None, pl.dt, ry.M, ry.C, 1)
+            if pl.lib.awr_bn_bwd_fused_ok(ry.M, ry.C, pl.dt, int(act is not None)):
+                pl.call(pl.bwd, "awr_bn_bwd_fused", dout, act, ry.t, self.bn_res.mi, pl.P(rp + ".weight"), None, self.bn_res.dsums, pl.arena(1), dry,
+                        dry if ry.gw else None, None, None, pl.G(rp + ".weight"), pl.G(rp + ".bias"), pl.dt, ry.M, ry.C, 1,
+                        tag="awr_bn_bwd_fused")
+            else:
+                pl.call(pl.bwd, "awr_bn_bwd_reduce", dout, act, ry.t, self.bn_res.mi, None, None, pl.dt, ry.M, ry.C, self.bn_res.dsums)
+                pl.call(pl.bwd, "awr_bn_bwd_apply", dout, act, ry.t, self.bn_res.mi, self.bn_res.dsums, pl.P(rp + ".weight"), dry,
+                        dry if ry.gw else None, None, None, pl.G(rp + ".weight"), pl.G(rp + ".bias"), None, pl.dt, ry.M, ry.C, 1)
             ry.gw = True
 
 

@@ -108,6 +108,17 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream);
 
+/* BN backward in ONE launch (both passes above) for tensors whose operands fit in the shared memory of one CTA per SM: every CTA stages its
+ * slice of dout / y (/ act_out) with 1-D bulk TMA copies, reduces, meets the other CTAs at a grid-wide barrier and writes dy / dres from the
+ * shared-memory copy.  `barrier`: one zero-initialised unsigned per call (re-zero before every launch; the plan keeps it in the per-step
+ * zeroed arena).  ReLU mask: recomputed from y when mask_beta is given (gamma is then the BN weight), else act_out > 0 when act_out is given,
+ * else none.  awr_bn_bwd_fused_ok returns 1 when the tensor qualifies (0: use awr_bn_bwd_reduce + awr_bn_bwd_apply); awr_bn_bwd_fused
+ * returns AWR_ERR_UNSUPPORTED otherwise.  The launch needs all its CTAs co-resident (grid <= SM count, one CTA per SM). */
+int awr_bn_bwd_fused_ok(long long M, int C, int dtype, int with_act);
+int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* gamma, const float* mask_beta,
+                     float* dsums, unsigned* barrier, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
+                     float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream);
+
 /* dx = dout*(act_out>0) [+ addend]   (act_out / addend may be NULL); n elements, n % 8 == 0 */
 int awr_relu_bwd(const void* dout, const void* act_out, const void* addend, void* dx, int dtype, long long n, void* stream);
 

@@ -489,6 +489,56 @@ maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restri
   }
 }
 
+// Pass 0 of the kernels above at POOLED resolution.  For out = MaxPool(ReLU(BN(y))) every pooling window w routes dpool[w] to its arg-max
+// pixel p(w), masked by ReLU: dz[p] = sum_{w: p(w)=p} dpool[w] * [a_p > 0] with a_p = out[w] (the pooled value IS the activation at the arg-max).
+// Hence  sum_p dz = sum_w dpool[w]*[out[w]>0]  and, because out[w] = gamma*yhat_p + beta wherever it is positive,
+//        sum_p dz*yhat = sum_w dpool[w]*[out[w]>0]*(out[w]-beta)/gamma :
+// both reductions need only the two pooled tensors (2 x 16.8 MB for the ResNet18 stem at 32 frames) instead of y + dpool + arg-max bytes at
+// full resolution (92 MB) and none of the window logic.  bf16 storage rounds out[w] (2^-9 relative on yhat, averaged over the batch);
+// a channel with gamma == 0 exactly contributes 0 to sum dz*yhat (its dy is 0 anyway).
+template <typename T, int U>
+__global__ void __launch_bounds__(kEwThreads, 2)
+pool_bn_bwd_reduce_kernel(const T* __restrict__ dpool, const T* __restrict__ pool_out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          long long M, int C, float* __restrict__ dsums) {
+  pdl_entry();
+  __shared__ float smem[kEwThreads * 8];
+  const int G = C >> 3;
+  const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
+  const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
+  const int c0 = (int)(first % G) * 8;
+  Raw8<T> rg[U], ro[U];
+  auto load_batch = [&](long long i0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < items) { rg[u].load(dpool + i * 8); ro[u].load(pool_out + i * 8); }
+    }
+  };
+  long long i0 = first;
+  if (i0 < items) load_batch(i0);
+  float ig[8], be[8];
+  load8f(gamma + c0, ig); load8f(beta + c0, be);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ig[k] = (fabsf(ig[k]) > 1e-20f) ? 1.0f / ig[k] : 0.f;
+  float acc[2][8] = {};
+  while (i0 < items) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= items) break;
+      float g[8], o[8];
+      rg[u].unpack(g); ro[u].unpack(o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dz = (o[k] > 0.f) ? g[k] : 0.f;
+        acc[0][k] += dz; acc[1][k] += dz * ((o[k] - be[k]) * ig[k]);
+      }
+    }
+    i0 += U * stride;
+    if (i0 < items) load_batch(i0);
+  }
+  block_channel_reduce<2>(acc, G, C, dsums, smem);
+}
+
 // MaxPool(3,2,1) specialisation of maxpool_bn_bwd_kernel (the ResNet stem): one thread owns a 2x2 block of full-resolution pixels
 // (x 8 channels); the four windows that can select any of them are loaded once and scattered with compile-time tap numbers.
 template <typename T>
@@ -1240,6 +1290,15 @@ int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* 
   return AWR_OK;
 }
 
+int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float* gamma, const float* beta, float* dsums, int dtype, long long M,
+                           int C, void* stream) {
+  AWR_HOST_CHECK(dpool && pool_out && gamma && beta && dsums && M > 0 && chan_ok(C));
+  DISPATCH_TU(dtype, launch_pdl(pool_bn_bwd_reduce_kernel<T, U>, dim3(ew_grid(M * (C / 8), U)), dim3(kEwThreads), 0, (cudaStream_t)stream,
+                                (const T*)dpool, (const T*)pool_out, gamma, beta, M, C, dsums));
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream) {
   AWR_HOST_CHECK(y && out && M > 0 && C % 8 == 0);
@@ -1273,8 +1332,6 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
 // geometry of the single-launch BN backward: grid (co-resident CTAs), items per CTA (multiple of 256), dynamic shared memory
 static bool bn_bwd_fused_geom(long long M, int C, int dtype, int with_act, int* grid, int* per, size_t* smem) {
   if (!chan_ok(C) || M <= 0 || (dtype != AWR_DTYPE_F32 && dtype != AWR_DTYPE_BF16)) return false;
-  static const bool off = [] { const char* e = getenv("AWR_BN_FUSED"); return e && e[0] == '0'; }();       // AWR_BN_FUSED=0: two-pass kernels only
-  if (off) return false;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 1; }
   const long long items = M * (C / 8);
@@ -1292,8 +1349,12 @@ static bool bn_bwd_fused_geom(long long M, int C, int dtype, int with_act, int* 
 
 /* 1 when awr_bn_bwd_fused can take this tensor (operands fit in one CTA per SM), else 0: the caller then uses reduce + apply. */
 int awr_bn_bwd_fused_ok(long long M, int C, int dtype, int with_act) {
+  // Opt-in (AWR_BN_FUSED=1).  Measured on B200, ResNet18 at 32 frames: 16 eligible layers, 14 us per single-launch kernel against 4 + 5 us
+  // for reduce + apply -- with one 256-thread CTA per SM the two shared-memory passes are bound by ALU latency (8 warps), which costs
+  // more than the saved launch and the saved second read (those tensors are L2 hits anyway).  The two-pass kernels stay the default.
+  static const bool on = [] { const char* e = getenv("AWR_BN_FUSED"); return e && e[0] == '1'; }();
   int g, p; size_t sm;
-  return bn_bwd_fused_geom(M, C, dtype, with_act, &g, &p, &sm) ? 1 : 0;
+  return (on && bn_bwd_fused_geom(M, C, dtype, with_act, &g, &p, &sm)) ? 1 : 0;
 }
 
 int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* gamma, const float* mask_beta,

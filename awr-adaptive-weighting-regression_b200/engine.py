@@ -676,9 +676,15 @@ class _BNPool(_Op):
         if not out.gw:
             return
         assert not y.gw
-        for ps in (0, 1):
+        # pass 0 (sum dz, sum dz*yhat) from the two POOLED tensors alone -- see pool_bn_bwd_reduce_kernel; AWR_B200_POOL_PASS0=full keeps the
+        # full-resolution reduction
+        if os.environ.get("AWR_B200_POOL_PASS0") == "full":
             pl.call(pl.bwd, "awr_maxpool_bn_bwd", out.grad(), self.idx, y.t, self.bn.mi, pl.P(pf + ".weight"), pl.P(pf + ".bias"), self.bn.dsums,
-                    y.grad(), pl.G(pf + ".weight"), pl.G(pf + ".bias"), pl.dt, y.N, y.H, y.W, y.C, self.k, self.s, self.p, ps, 1)
+                    y.grad(), pl.G(pf + ".weight"), pl.G(pf + ".bias"), pl.dt, y.N, y.H, y.W, y.C, self.k, self.s, self.p, 0, 1)
+        else:
+            pl.call(pl.bwd, "awr_pool_bn_bwd_reduce", out.grad(), out.t, pl.P(pf + ".weight"), pl.P(pf + ".bias"), self.bn.dsums, pl.dt, out.M, out.C)
+        pl.call(pl.bwd, "awr_maxpool_bn_bwd", out.grad(), self.idx, y.t, self.bn.mi, pl.P(pf + ".weight"), pl.P(pf + ".bias"), self.bn.dsums,
+                y.grad(), pl.G(pf + ".weight"), pl.G(pf + ".bias"), pl.dt, y.N, y.H, y.W, y.C, self.k, self.s, self.p, 1, 1)
         y.gw = True
 
 

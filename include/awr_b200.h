@@ -92,6 +92,12 @@ int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* 
                        const float* beta, float* dsums, void* dy, float* dgamma, float* dbeta, int dtype, int N, int H, int W, int C, int k,
                        int s, int p, int pass, int accumulate_param_grads, void* stream);
 
+/* Pass 0 of awr_maxpool_bn_bwd at pooled resolution (any k/s/p): dsums[0:C] += sum dpool*[pool_out>0], dsums[C:2C] += sum dpool*[pool_out>0]*
+ * (pool_out-beta)/gamma, which equal sum dz and sum dz*yhat of the full-resolution pass because the pooled value is the activation at the
+ * arg-max pixel.  dpool / pool_out: (M = N*Ho*Wo, C) NHWC. */
+int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float* gamma, const float* beta, float* dsums, int dtype, long long M,
+                           int C, void* stream);
+
 /* out = act( ss(y) + res_ss(res) ),  ss(v)[c] = v*scale[c] + shift[c]; scale_shift / res / res_scale_shift may be NULL. */
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream);
@@ -112,8 +118,9 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
  * slice of dout / y (/ act_out) with 1-D bulk TMA copies, reduces, meets the other CTAs at a grid-wide barrier and writes dy / dres from the
  * shared-memory copy.  `barrier`: one zero-initialised unsigned per call (re-zero before every launch; the plan keeps it in the per-step
  * zeroed arena).  ReLU mask: recomputed from y when mask_beta is given (gamma is then the BN weight), else act_out > 0 when act_out is given,
- * else none.  awr_bn_bwd_fused_ok returns 1 when the tensor qualifies (0: use awr_bn_bwd_reduce + awr_bn_bwd_apply); awr_bn_bwd_fused
- * returns AWR_ERR_UNSUPPORTED otherwise.  The launch needs all its CTAs co-resident (grid <= SM count, one CTA per SM). */
+ * else none.  awr_bn_bwd_fused returns AWR_ERR_UNSUPPORTED when the operands do not fit; awr_bn_bwd_fused_ok returns 1 when the tensor
+ * qualifies AND the path is enabled (AWR_BN_FUSED=1; measured slower than reduce + apply at the headline sizes, so off by default).
+ * The launch needs all its CTAs co-resident (grid <= SM count, one CTA per SM). */
 int awr_bn_bwd_fused_ok(long long M, int C, int dtype, int with_act);
 int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* gamma, const float* mask_beta,
                      float* dsums, unsigned* barrier, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,

@@ -19,9 +19,11 @@ def _run(lib, L, fused, dt, dout, act, y, mi, gamma, beta, remask, dy_add, want_
     a = None if remask else act
     if fused:
         bar = torch.zeros(1, dtype=torch.int32, device="cuda")
-        assert lib.awr_bn_bwd_fused_ok(M, C, dt, int(a is not None)) == 1
-        L.check(lib.awr_bn_bwd_fused(p(dout), p(a), p(y), p(mi), p(gamma), p(mb), p(dsums), p(bar), p(dy), p(dy) if dy_add is not None else None,
-                                     p(dres), p(dres) if dres_add is not None else None, p(dg), p(db), dt, M, C, 1, L.stream()), "fused")
+        rc = lib.awr_bn_bwd_fused(p(dout), p(a), p(y), p(mi), p(gamma), p(mb), p(dsums), p(bar), p(dy), p(dy) if dy_add is not None else None,
+                                  p(dres), p(dres) if dres_add is not None else None, p(dg), p(db), dt, M, C, 1, L.stream())
+        if rc == -2:
+            pytest.skip("operands do not fit in one CTA per SM: two-pass kernels only")
+        L.check(rc, "fused")
     else:
         L.check(lib.awr_bn_bwd_reduce(p(dout), p(a), p(y), p(mi), p(mg), p(mb), dt, M, C, p(dsums), L.stream()), "reduce")
         L.check(lib.awr_bn_bwd_apply(p(dout), p(a), p(y), p(mi), p(dsums), p(gamma), p(dy), p(dy) if dy_add is not None else None, p(dres),

@@ -35,7 +35,7 @@ inline int ew_grid(long long items, int U) {
   if (b > 148 * 4) b = 148 * 4;
   return (int)b;
 }
-// loads in flight per thread and tensor of the BatchNorm passes (AWR_EW_UNROLL=1|2|4 overrides; 1 = one 16-byte load at a time)
+// 16-byte loads in flight per thread and tensor of the BatchNorm passes: two register batches of U/2 items (AWR_EW_UNROLL=2|4; default 4)
 inline int ew_unroll() {
   static const int u = [] { const char* e = getenv("AWR_EW_UNROLL"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
   return u;
@@ -238,23 +238,26 @@ bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSe
   const long long items = M * G, stride = (long long)(gridDim.x - 1) * kEwThreads;
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   const int c0 = (int)(first % G) * 8;
-  // U items per thread and iteration; every load of a batch is issued before its first use, and the first batch is issued BEFORE the
-  // per-channel coefficient loads so that the two dependent DRAM/L2 round trips of a small tensor overlap
-  Raw8<T> ry[U], rr[U];
-  auto load_batch = [&](long long i0) {
+  // U items per thread and batch, two register batches: the loads of batch k+1 are issued before batch k is consumed (loads stay in
+  // flight during the arithmetic and the stores), and the first batch is issued BEFORE the per-channel coefficient loads so that the two
+  // dependent DRAM/L2 round trips of a small tensor overlap
+  Raw8<T> ya[U], ra[U], yb[U], rb[U];
+  auto load_batch = [&](Raw8<T> (&ry)[U], Raw8<T> (&rr)[U], long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
       if (i < items) { ry[u].load(y + i * 8); if (res) rr[u].load(res + i * 8); }
     }
   };
+  const long long step = (long long)U * stride;
   long long i0 = first;
-  if (i0 < items) load_batch(i0);
+  if (i0 < items) load_batch(ya, ra, i0);
+  if (i0 + step < items) load_batch(yb, rb, i0 + step);
   const float inv_count = 1.0f / count;
   float sc[8], sh[8], rsc[8], rsh[8];
   bn_coeffs8(bn, c0, C, inv_count, eps, training, sc, sh);
   if (res_has_bn) bn_coeffs8(rbn, c0, C, inv_count, eps, training, rsc, rsh);
-  while (i0 < items) {
+  auto process = [&](const Raw8<T> (&ry)[U], const Raw8<T> (&rr)[U], long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
@@ -279,8 +282,15 @@ bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSe
       }
       Vec8<T>::store(out + i * 8, v);
     }
-    i0 += U * stride;
-    if (i0 < items) load_batch(i0);
+  };
+  while (i0 < items) {
+    process(ya, ra, i0);
+    if (i0 + 2 * step < items) load_batch(ya, ra, i0 + 2 * step);
+    i0 += step;
+    if (i0 >= items) break;
+    process(yb, rb, i0);
+    if (i0 + 2 * step < items) load_batch(yb, rb, i0 + 2 * step);
+    i0 += step;
   }
 }
 
@@ -654,8 +664,8 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   const int c0 = (int)(first % G) * 8;
   const bool use_act = !mask_gamma && act_out;
-  Raw8<T> rg[U], ry[U], ra[U];
-  auto load_batch = [&](long long i0) {
+  Raw8<T> ga[U], ya[U], aa[U], gb[U], yb[U], ab[U];      // two register batches (see bn_act_kernel)
+  auto load_batch = [&](Raw8<T> (&rg)[U], Raw8<T> (&ry)[U], Raw8<T> (&ra)[U], long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
@@ -665,16 +675,19 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
       }
     }
   };
+  const long long step = (long long)U * stride;
   long long i0 = first;
-  if (i0 < items) load_batch(i0);          // in flight while the per-channel constants are fetched
+  if (i0 < items) load_batch(ga, ya, aa, i0);          // in flight while the per-channel constants are fetched
+  if (i0 + step < items) load_batch(gb, yb, ab, i0 + step);
   float mean[8], istd[8], msc[8], msh[8];
+  load8f(mean_invstd + c0, mean); load8f(mean_invstd + C + c0, istd);
+  if (mask_gamma) {
+    load8f(mask_gamma + c0, msc); load8f(mask_beta + c0, msh);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k];
-    if (mask_gamma) { msc[k] = mask_gamma[c0 + k] * istd[k]; msh[k] = mask_beta[c0 + k] - mean[k] * msc[k]; }
+    for (int k = 0; k < 8; ++k) { msc[k] *= istd[k]; msh[k] -= mean[k] * msc[k]; }
   }
   float acc[2][8] = {};
-  while (i0 < items) {
+  auto process = [&](const Raw8<T> (&rg)[U], const Raw8<T> (&ry)[U], const Raw8<T> (&ra)[U], long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (i0 + u * stride >= items) break;
@@ -692,8 +705,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
 #pragma unroll
       for (int k = 0; k < 8; ++k) { acc[0][k] += g[k]; acc[1][k] += g[k] * (yy[k] - mean[k]) * istd[k]; }
     }
-    i0 += U * stride;
-    if (i0 < items) load_batch(i0);
+  };
+  while (i0 < items) {
+    process(ga, ya, aa, i0);
+    if (i0 + 2 * step < items) load_batch(ga, ya, aa, i0 + 2 * step);
+    i0 += step;
+    if (i0 >= items) break;
+    process(gb, yb, ab, i0);
+    if (i0 + 2 * step < items) load_batch(gb, yb, ab, i0 + 2 * step);
+    i0 += step;
   }
   block_channel_reduce<2>(acc, G, C, dsums, smem);
 }
@@ -722,42 +742,46 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
   const long long first = (long long)blockIdx.x * kEwThreads + threadIdx.x;
   const int c0 = (int)(first % G) * 8;
   const bool use_act = !mask_beta && act_out, add_res = dres && dres_addend;
-  Raw8<T> rg[U], ry[U], ra[U], rb[U], rc[U];
-  auto load_batch = [&](long long i0) {
+  struct Batch { Raw8<T> g[U], y[U], a[U], b[U], c[U]; };
+  Batch ba, bb;                                          // two register batches (see bn_act_kernel)
+  auto load_batch = [&](Batch& t, long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
       if (i < items) {
-        rg[u].load(dout + i * 8); ry[u].load(y + i * 8);
-        if (use_act) ra[u].load(act_out + i * 8);
-        if (add_res) rb[u].load(dres_addend + i * 8);
-        if (dy_addend) rc[u].load(dy_addend + i * 8);
+        t.g[u].load(dout + i * 8); t.y[u].load(y + i * 8);
+        if (use_act) t.a[u].load(act_out + i * 8);
+        if (add_res) t.b[u].load(dres_addend + i * 8);
+        if (dy_addend) t.c[u].load(dy_addend + i * 8);
       }
     }
   };
+  const long long step = (long long)U * stride;
   long long i0 = first;
-  if (i0 < items) load_batch(i0);          // in flight while the per-channel constants are fetched
+  if (i0 < items) load_batch(ba, i0);          // in flight while the per-channel constants are fetched
+  if (i0 + step < items) load_batch(bb, i0 + step);
   const float invM = 1.0f / (float)M;
   float mean[8], istd[8], k1[8], k2[8], gs[8], msh[8];
+  load8f(mean_invstd + c0, mean); load8f(mean_invstd + C + c0, istd); load8f(dsums + c0, k1); load8f(dsums + C + c0, k2); load8f(gamma + c0, gs);
+  if (mask_beta) load8f(mask_beta + c0, msh);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    mean[k] = mean_invstd[c0 + k]; istd[k] = mean_invstd[C + c0 + k];
-    k1[k] = dsums[c0 + k] * invM; k2[k] = dsums[C + c0 + k] * invM; gs[k] = gamma[c0 + k] * istd[k];
-    msh[k] = mask_beta ? mask_beta[c0 + k] - mean[k] * gs[k] : 0.f;
+    k1[k] *= invM; k2[k] *= invM; gs[k] *= istd[k];
+    msh[k] = mask_beta ? msh[k] - mean[k] * gs[k] : 0.f;
   }
-  while (i0 < items) {
+  auto process = [&](const Batch& t, long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + u * stride;
       if (i >= items) break;
       float g[8], yy[8];
-      rg[u].unpack(g); ry[u].unpack(yy);
+      t.g[u].unpack(g); t.y[u].unpack(yy);
       if (mask_beta) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = (from_store<T>(fmaxf(yy[k] * gs[k] + msh[k], 0.f)) > 0.f) ? g[k] : 0.f;
       } else if (act_out) {
         float a[8];
-        ra[u].unpack(a);
+        t.a[u].unpack(a);
 #pragma unroll
         for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
       }
@@ -767,7 +791,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
       if (dres) {
         if (dres_addend) {
           float b[8];
-          rb[u].unpack(b);
+          t.b[u].unpack(b);
 #pragma unroll
           for (int k = 0; k < 8; ++k) g[k] += b[k];
         }
@@ -775,14 +799,21 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
       }
       if (dy_addend) {
         float b[8];
-        rc[u].unpack(b);
+        t.c[u].unpack(b);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] += b[k];
       }
       Vec8<T>::store(dy + i * 8, o);
     }
-    i0 += U * stride;
-    if (i0 < items) load_batch(i0);
+  };
+  while (i0 < items) {
+    process(ba, i0);
+    if (i0 + 2 * step < items) load_batch(ba, i0 + 2 * step);
+    i0 += step;
+    if (i0 >= items) break;
+    process(bb, i0);
+    if (i0 + 2 * step < items) load_batch(bb, i0 + 2 * step);
+    i0 += step;
   }
 }
 
@@ -1246,7 +1277,7 @@ int awr_bn_act(const void* y, const float* sums, const float* gamma, const float
   AWR_HOST_CHECK(!res_has_bn || (res && res_beta && (training ? (res_sums != nullptr) : (res_running_mean && res_running_var))));
   BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
   BnSet b{res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
-  DISPATCH_TU(dtype, launch_pdl(bn_act_kernel<T, U>, dim3(ew_grid(M * (C / 8), U) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a,
+  DISPATCH_TU(dtype, launch_pdl(bn_act_kernel<T, (U >= 4 ? 2 : 1)>, dim3(ew_grid(M * (C / 8), (U >= 4 ? 4 : 2)) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a,
                                 (const T*)res, b, res_has_bn, (T*)out, M, C, (float)M, momentum, eps, training, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1293,7 +1324,7 @@ int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* 
 int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float* gamma, const float* beta, float* dsums, int dtype, long long M,
                            int C, void* stream) {
   AWR_HOST_CHECK(dpool && pool_out && gamma && beta && dsums && M > 0 && chan_ok(C));
-  DISPATCH_TU(dtype, launch_pdl(pool_bn_bwd_reduce_kernel<T, U>, dim3(ew_grid(M * (C / 8), U)), dim3(kEwThreads), 0, (cudaStream_t)stream,
+  DISPATCH_TU(dtype, launch_pdl(pool_bn_bwd_reduce_kernel<T, (U >= 4 ? 2 : 1)>, dim3(ew_grid(M * (C / 8), (U >= 4 ? 4 : 2))), dim3(kEwThreads), 0, (cudaStream_t)stream,
                                 (const T*)dpool, (const T*)pool_out, gamma, beta, M, C, dsums));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1311,7 +1342,7 @@ int awr_affine_act(const void* y, const float* scale_shift, const void* res, con
 int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* mask_gamma,
                       const float* mask_beta, int dtype, long long M, int C, float* dsums, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && M > 0 && chan_ok(C) && ((mask_gamma == nullptr) == (mask_beta == nullptr)));
-  DISPATCH_TU(dtype, launch_pdl(bn_bwd_reduce_kernel<T, U>, dim3(ew_grid(M * (C / 8), U)), dim3(kEwThreads), 0, (cudaStream_t)stream,
+  DISPATCH_TU(dtype, launch_pdl(bn_bwd_reduce_kernel<T, (U >= 4 ? 2 : 1)>, dim3(ew_grid(M * (C / 8), (U >= 4 ? 4 : 2))), dim3(kEwThreads), 0, (cudaStream_t)stream,
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, dsums, mask_gamma, mask_beta));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1321,8 +1352,8 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && gamma && dy && M > 0 && chan_ok(C));
-  // up to five tensors are read per item here: two items per batch keep the kernel at 128 registers = 2 CTAs per SM
-  DISPATCH_TU(dtype, launch_pdl(bn_bwd_apply_kernel<T, (U > 2 ? 2 : U)>, dim3(ew_grid(M * (C / 8), (U > 2 ? 2 : U)) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream,
+  // up to five tensors are read per item here: half the batch depth of the other passes keeps the kernel at 128 registers = 2 CTAs per SM
+  DISPATCH_T(dtype, launch_pdl(bn_bwd_apply_kernel<T, 1>, dim3(ew_grid(M * (C / 8), 2) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream,
                         (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
                         (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads, mask_beta));
   AWR_LAUNCH_CHECK();

@@ -313,6 +313,10 @@ class Plan:
             raise RuntimeError("plan arena exhausted")
         return self.arena_buf[off: off + n]
 
+    def arena_used(self):
+        """The carved part of the arena (what a step has to re-zero)."""
+        return self.arena_buf[: max(self._arena_total, 64)]
+
     def call(self, lst, fn, *args, flops=0, nbytes=0, tag=None, detail="", side=False):
         """Bind a C-ABI launch. Tensor-like args are resolved to pointers now (buffers are static).
         flops / nbytes: algorithmic work of this launch (for the roofline report); tag: kernel class label."""

@@ -141,7 +141,7 @@ class _BackboneFn(torch.autograd.Function):
         if pl.precision == "bf16":
             st.refresh_shadow()
         pl.img.copy_(x.detach().to(torch.float32))
-        pl.arena_buf.zero_()
+        pl.arena_used().zero_()
         pl.run_forward()
         pl.version += 1
         ctx.module, ctx.pl, ctx.version = module, pl, pl.version

@@ -66,7 +66,7 @@ class FusedTrainer:
         if part == 1:
             pl.run_backward(s, side=self.side, part=1)
             return
-        pl.arena_buf.zero_()
+        pl.arena_used().zero_()
         st.grads.zero_()
         for h in pl.heads[:-1]:
             h.dpred.zero_()

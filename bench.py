@@ -216,7 +216,7 @@ def classify_step(tr, steps, layers=None):
         evs = []
         s = L.stream()
         torch.cuda._sleep(int(40e6))          # ~20 ms: lets the host enqueue the whole step so events are back-to-back
-        pl.arena_buf.zero_(); tr.store.grads.zero_()
+        pl.arena_used().zero_(); tr.store.grads.zero_()
         seq = [(f, m) for f, m in zip(pl.fwd, pl.fwd_meta)]
         hd = tr.head
         lib = tr.lib

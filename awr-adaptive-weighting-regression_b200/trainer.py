@@ -53,6 +53,7 @@ class FusedTrainer:
         self.steps_done = 0
         self.use_graph = use_graph
         self.graph_fb = self.graph_opt = None
+        self._pipe = None
         self.side = torch.cuda.Stream(device=dev)          # weight-gradient GEMMs overlap the dgrad / BatchNorm backward chain
         if self.plan.precision == "bf16":
             self.store.refresh_shadow()
@@ -159,6 +160,58 @@ class FusedTrainer:
         self.loss_host.copy_(self.loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host[0]), float(self.loss_host[1])
+
+    # ---- pipelined form of train_step: the host never waits for the step it has just enqueued -------------------------------
+    def submit(self, img, jt_uvd_gt):
+        """Enqueue one optimisation step on a host (pinned) or device batch and return immediately.  The H2D copy runs on a copy
+        stream into one of two staging slots, so it overlaps the previous step's kernels; the step's losses are copied D2H behind it
+        and are returned by the matching collect().  At most two steps may be outstanding (submit, submit, collect, submit, ...)."""
+        if self._pipe is None:
+            dev, B, H, J = self.device, self.B, self.H, self.J
+            self._pipe = {
+                "copy": torch.cuda.Stream(device=dev),
+                "img": [torch.empty(B, 1, H, H, dtype=torch.float32, device=dev) for _ in range(2)],
+                "jt": [torch.empty(B, J, 3, dtype=torch.float32, device=dev) for _ in range(2)],
+                "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
+                "done": [torch.cuda.Event() for _ in range(2)],
+                "loss": [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)],
+                "submitted": 0, "collected": 0}
+        pp = self._pipe
+        if pp["submitted"] - pp["collected"] >= 2:
+            raise RuntimeError("FusedTrainer.submit: two steps already outstanding; call collect() first")
+        slot = pp["submitted"] % 2
+        main, cs = torch.cuda.current_stream(), pp["copy"]
+        cs.wait_event(pp["free"][slot])                     # the step that last used this slot has copied it out (no-op the first time)
+        with torch.cuda.stream(cs):
+            pp["img"][slot].copy_(img.view(self.B, 1, self.H, self.H), non_blocking=True)
+            pp["jt"][slot].copy_(jt_uvd_gt, non_blocking=True)
+            pp["ready"][slot].record(cs)
+        main.wait_event(pp["ready"][slot])
+        self.plan.img.copy_(pp["img"][slot], non_blocking=True)
+        self.jt.copy_(pp["jt"][slot], non_blocking=True)
+        pp["free"][slot].record(main)
+        self.run_step()
+        pp["loss"][slot].copy_(self.loss, non_blocking=True)
+        pp["done"][slot].record(main)
+        pp["submitted"] += 1
+
+    def collect(self):
+        """(loss_coord, loss_dense) of the oldest submitted step not collected yet; blocks until that step has finished."""
+        pp = self._pipe
+        if pp is None or pp["collected"] >= pp["submitted"]:
+            raise RuntimeError("FusedTrainer.collect: nothing outstanding")
+        slot = pp["collected"] % 2
+        pp["done"][slot].synchronize()
+        pp["collected"] += 1
+        return float(pp["loss"][slot][0]), float(pp["loss"][slot][1])
+
+    def train_step_lagged(self, img, jt_uvd_gt):
+        """train_step with one step of lag on the logged losses: enqueues this batch and returns the losses of the PREVIOUS call (None on
+        the first).  Same work per call as train_step -- H2D of this batch, the step, D2H of its losses -- but the host read never
+        drains the queue, so the copy of batch k+1 and the launch of step k+1 overlap step k.  Finish with collect()."""
+        self.submit(img, jt_uvd_gt)
+        pp = self._pipe
+        return self.collect() if pp["submitted"] - pp["collected"] == 2 else None
 
     def broadcast_parameters(self, src=0):
         """DDP-style start: every replica takes rank `src`'s parameters and BN buffers."""

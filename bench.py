@@ -6,8 +6,8 @@
 
 A step = one full train.py:107-131 iteration (GT volume, backbone fwd, AWR head, joint+dense SmoothL1, backward,
 [NCCL grad all-reduce], Adam) over one synthetic batch of `--batch` 128x128 depth crops per GPU, 14 joints.
-Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same step through FusedTrainer.train_step
-with pinned HOST buffers (H2D of the batch + D2H of the losses inside the timed region).
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same step through FusedTrainer.train_step_lagged
+with pinned HOST buffers (H2D of every batch + D2H of every step's losses inside the timed region; losses are handed back one call late).
 `--impl reference` times the CPU port of the reference's own path (oracle/) on the host cores.
 """
 import argparse
@@ -373,8 +373,11 @@ def main():
         tr.train_step(*host_batches[w % 4])
     barrier()
     e0.record()
-    for k in range(a.steps):
-        lc, ld = tr.train_step(*host_batches[k % 4])
+    for k in range(a.steps):                     # every step: H2D of its batch (pinned host), the step, D2H of its two losses
+        r = tr.train_step_lagged(*host_batches[k % 4])
+        if r is not None:
+            lc, ld = r
+    lc, ld = tr.collect()                         # the last step's losses: read inside the timed region too
     e1.record()
     barrier()
     t2 = time.perf_counter()
@@ -443,7 +446,7 @@ def main():
         act_bytes = sum(op.y.t.numel() * op.y.t.element_size() for op in tr.plan.ops if hasattr(op, "y"))
         cfg = workload_config(a, world)
         cfg.update({"precision": a.precision, "l2": f"no flush needed: per-step conv outputs alone are {act_bytes / 2**20:.0f} MiB (> 126 MB L2), "
-                    "rotating 4 input batches", "cuda_graph": not a.no_graph, "e2e_api": "awr_b200.trainer.FusedTrainer.train_step(pinned host img, jt)"})
+                    "rotating 4 input batches", "cuda_graph": not a.no_graph, "e2e_api": "awr_b200.trainer.FusedTrainer.train_step_lagged(pinned host img, jt) -> losses of the previous step; collect() at the end"})
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.precision, "data": "synthetic", "config": cfg, "clocks": clocks,

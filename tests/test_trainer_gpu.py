@@ -81,3 +81,35 @@ def test_fused_step_fp32_vs_oracle(net, ks):
     assert tr.step_dev.item() == 1.0
     od = tr.optimizer_state_dict()
     assert len(od["state"]) == len(list(m.parameters())) and od["param_groups"][0]["lr"] == 1e-3
+
+
+def test_lagged_pipeline_matches_blocking_steps():
+    """train_step_lagged / submit / collect (H2D on a copy stream, losses one call late) runs the same optimisation as train_step."""
+    import awr_b200
+    from awr_b200.trainer import FusedTrainer
+    B, H, J, ds, ks = 2, 128, 14, 2, 1.0
+    sd = O.randomize_bn(O.resnet_deconv_init(18, J, ds, 31, head_std=0.02), 32)
+    batches = [tuple(t.pin_memory() for t in O.synthetic_batch(B, H, J, 40 + i)) for i in range(4)]
+    results = []
+    for lagged in (False, True):
+        m = awr_b200.get_deconv_net(18, J, ds, precision="fp32")
+        m.load_state_dict(sd, strict=True)
+        tr = FusedTrainer(m.cuda(), B, H, ks, 1.0, 1.0, lr=1e-3, use_graph=True)
+        tr.load_batch(*batches[0])
+        tr._capture()
+        m.load_state_dict(sd, strict=True)            # capture warm-ups advanced the BN running statistics
+        out = []
+        if lagged:
+            for b in batches:
+                r = tr.train_step_lagged(*b)
+                if r is not None:
+                    out.append(r)
+            out.append(tr.collect())
+            with pytest.raises(RuntimeError):
+                tr.collect()
+        else:
+            out = [tr.train_step(*b) for b in batches]
+        results.append(out)
+    assert len(results[0]) == len(results[1]) == 4
+    for (a0, a1), (b0, b1) in zip(*results):
+        assert abs(a0 - b0) <= 1e-3 * abs(a0) + 1e-9 and abs(a1 - b1) <= 1e-3 * abs(a1) + 1e-9

@@ -89,7 +89,12 @@ def test_lagged_pipeline_matches_blocking_steps():
     from awr_b200.trainer import FusedTrainer
     B, H, J, ds, ks = 2, 128, 14, 2, 1.0
     sd = O.randomize_bn(O.resnet_deconv_init(18, J, ds, 31, head_std=0.02), 32)
-    batches = [tuple(t.pin_memory() for t in O.synthetic_batch(B, H, J, 40 + i)) for i in range(4)]
+    # batches with very different targets (joints shifted by 0.15*i): a step run on the wrong batch would change its losses by far
+    # more than the few per cent that fp32 atomics + Adam's sign-like first updates make two identical runs drift apart
+    batches = []
+    for i in range(4):
+        img, jt = O.synthetic_batch(B, H, J, 40 + i)
+        batches.append((img.pin_memory(), (jt + 0.15 * i).pin_memory()))
     results = []
     for lagged in (False, True):
         m = awr_b200.get_deconv_net(18, J, ds, precision="fp32")
@@ -111,5 +116,8 @@ def test_lagged_pipeline_matches_blocking_steps():
             out = [tr.train_step(*b) for b in batches]
         results.append(out)
     assert len(results[0]) == len(results[1]) == 4
-    for (a0, a1), (b0, b1) in zip(*results):
-        assert abs(a0 - b0) <= 1e-3 * abs(a0) + 1e-9 and abs(a1 - b1) <= 1e-3 * abs(a1) + 1e-9
+    for k, ((a0, a1), (b0, b1)) in enumerate(zip(*results)):
+        tol = 1e-3 if k == 0 else 5e-2          # step 0 starts from identical parameters
+        assert abs(a0 - b0) <= tol * abs(a0) + 1e-9 and abs(a1 - b1) <= tol * abs(a1) + 1e-9, (k, results)
+    coord = [r[0] for r in results[0]]
+    assert max(coord) > 2.0 * min(coord)        # the batches really are distinguishable by their losses

@@ -1,10 +1,15 @@
 #!/bin/bash
-# Round-1 final ncu evidence (one GPU, under gpurun): full-set captures of the tensor-core conv kernels and the head kernels.
+# Round-1 final ncu evidence (one GPU, under gpurun): launch list of one eager step + full-set captures of the tensor-core conv kernels,
+# the fused head kernels and the large BatchNorm passes.  Summaries go to profiles/ via tools/summarize_ncu.py.
 set -u
-TAG=${1:-r01_final}
-mkdir -p gpurun_out
-BENCH="python bench.py --steps 1 --warmup 3 --cpu-steps 0 --no-graph"
-ncu --set full --clock-control none --import-source on -k regex:conv_halo_kernel -s 136 -c 13 -f -o gpurun_out/prof_${TAG}_halo $BENCH > gpurun_out/prof_${TAG}_halo.log 2>&1
-ncu --set full --clock-control none -k regex:wgrad_tc_kernel -s 116 -c 4 -f -o gpurun_out/prof_${TAG}_wgrad $BENCH > gpurun_out/prof_${TAG}_wgrad.log 2>&1
-ncu --set full --clock-control none -k regex:head_ -s 8 -c 2 -f -o gpurun_out/prof_${TAG}_head $BENCH > gpurun_out/prof_${TAG}_head.log 2>&1
-ls -la gpurun_out | grep ${TAG}
+TAG=${1:-r01_final2}
+O=gpurun_out; mkdir -p $O
+BENCH="python bench.py --steps 1 --warmup 3 --cpu-steps 0 --no-graph --no-parity"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/launches_${TAG}.csv $BENCH > $O/launches_${TAG}.log 2>&1
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:conv_halo_kernel -s 136 -c 8 -f -o $O/prof_${TAG}_halo $BENCH > $O/prof_${TAG}_halo.log 2>&1
+timeout 120 ncu --set full --clock-control none -k regex:wgrad_tc_kernel -s 116 -c 4 -f -o $O/prof_${TAG}_wgrad $BENCH > $O/prof_${TAG}_wgrad.log 2>&1
+timeout 120 ncu --set full --clock-control none -k regex:'head_fwd_kernel|head_bwd_kernel' -s 8 -c 2 -f -o $O/prof_${TAG}_head $BENCH > $O/prof_${TAG}_head.log 2>&1
+timeout 150 ncu --set full --clock-control none -k regex:'bn_act_kernel|bn_bwd_reduce_kernel|bn_bwd_apply_kernel|pool_bn_bwd_reduce|stem_conv_tiled|stem_wgrad_pair|maxpool3' -s 69 -c 12 -f -o $O/prof_${TAG}_ew $BENCH > $O/prof_${TAG}_ew.log 2>&1
+for k in halo wgrad head ew; do ncu -i $O/prof_${TAG}_$k.ncu-rep --page raw --csv > $O/prof_${TAG}_$k.csv 2>/dev/null; done
+rm -f $O/prof_${TAG}_wgrad.ncu-rep $O/prof_${TAG}_ew.ncu-rep
+ls -la $O | grep ${TAG}

@@ -89,8 +89,7 @@ def test_lagged_pipeline_matches_blocking_steps():
     from awr_b200.trainer import FusedTrainer
     B, H, J, ds, ks = 2, 128, 14, 2, 1.0
     sd = O.randomize_bn(O.resnet_deconv_init(18, J, ds, 31, head_std=0.02), 32)
-    # batches with very different targets (joints shifted by 0.15*i): a step run on the wrong batch would change its losses by far
-    # more than the few per cent that fp32 atomics + Adam's sign-like first updates make two identical runs drift apart
+    # batches with very different targets (joints shifted by 0.15*i): a step run on the wrong batch changes its losses by tens of per cent
     batches = []
     for i in range(4):
         img, jt = O.synthetic_batch(B, H, J, 40 + i)
@@ -99,7 +98,9 @@ def test_lagged_pipeline_matches_blocking_steps():
     for lagged in (False, True):
         m = awr_b200.get_deconv_net(18, J, ds, precision="fp32")
         m.load_state_dict(sd, strict=True)
-        tr = FusedTrainer(m.cuda(), B, H, ks, 1.0, 1.0, lr=1e-3, use_graph=True)
+        # lr 1e-6: Adam's first updates are sign-like (|delta| ~ lr whatever the gradient), so with a normal lr the fp32-atomic noise of
+        # two identical runs flips near-zero gradient signs and the losses drift by several per cent within three steps
+        tr = FusedTrainer(m.cuda(), B, H, ks, 1.0, 1.0, lr=1e-6, use_graph=True)
         tr.load_batch(*batches[0])
         tr._capture()
         m.load_state_dict(sd, strict=True)            # capture warm-ups advanced the BN running statistics
@@ -117,7 +118,7 @@ def test_lagged_pipeline_matches_blocking_steps():
         results.append(out)
     assert len(results[0]) == len(results[1]) == 4
     for k, ((a0, a1), (b0, b1)) in enumerate(zip(*results)):
-        tol = 1e-3 if k == 0 else 5e-2          # step 0 starts from identical parameters
+        tol = 1e-3
         assert abs(a0 - b0) <= tol * abs(a0) + 1e-9 and abs(a1 - b1) <= tol * abs(a1) + 1e-9, (k, results)
     coord = [r[0] for r in results[0]]
     assert max(coord) > 2.0 * min(coord)        # the batches really are distinguishable by their losses

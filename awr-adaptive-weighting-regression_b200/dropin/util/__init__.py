@@ -1,4 +1,4 @@
-"""`util` package shim: feature_tool comes from awr_b200; eval_tool / vis_tool / util keep resolving to the reference
+"""`util` package shim: feature_tool and eval_tool come from awr_b200; vis_tool / util keep resolving to the reference
 checkout further down sys.path."""
 from pkgutil import extend_path
 

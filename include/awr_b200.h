@@ -57,6 +57,21 @@ int awr_huber_fwd(const float* x, const float* y, long long n, float* ws, float*
 /* d/dx of the above times *grad_out (device scalar, NULL == 1). */
 int awr_huber_bwd(const float* x, const float* y, long long n, const float* grad_out, float* dx, void* stream);
 
+/* ---- evaluation of predicted joints (util/eval_tool.py:20-122, util/util.py:13-20) -------------------------------- */
+
+/* EvalUtil.feed for a batch.  uvd_pred (B,J,3) normalised crop coordinates; xyz_gt_norm (B,J,3) cube-normalised GT; center_xyz (B,3) mm;
+ * M (B,3,3) crop affine; cube (B,3) mm; vis (B,J) bytes or NULL (all visible).  Outputs: uvd_img (B,J,3) = pixel u, v in the original
+ * image + depth in mm (what test.py:103-108 writes to results/*.txt); dist (B,J) Euclidean error in mm, -1 where not visible;
+ * diff_mean (B,3) or NULL = mean signed error per frame (eval_tool.py:50). */
+int awr_eval_feed(const float* uvd_pred, const float* xyz_gt_norm, const float* center_xyz, const float* M, const float* cube,
+                  const unsigned char* vis, int B, int J, float img_size, float fx, float fy, float fu, float fv, float flip, float* uvd_img,
+                  float* dist, float* diff_mean, void* stream);
+
+/* Reductions of EvalUtil.get_measures over dist (N,J) (entries < 0 ignored): sum[J] (double) and count[J] of the errors per joint and
+ * pck_count[J][nthr] = number of errors <= linspace(0, thr_max, nthr)[k]. */
+int awr_eval_measures(const float* dist, long long N, int J, int nthr, float thr_max, double* sum, unsigned* count, unsigned* pck_count,
+                      void* stream);
+
 /* ---- NHWC elementwise / normalisation kernels (storage dtype: AWR_DTYPE_F32 or AWR_DTYPE_BF16) ---------------
  * Internal activation layout is NHWC (M = N*H*W pixels x C channels, C a power of two in [64,2048] for the
  * per-channel reductions).  These replace nn.BatchNorm2d / nn.ReLU / residual adds / nn.MaxPool2d / nn.Upsample

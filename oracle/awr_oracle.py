@@ -430,6 +430,76 @@ def mean_3d_error_mm(jt_uvd_pred, jt_xyz_gt_norm, center_xyz, M, cube, img_size)
 
 
 # --------------------------------------------------------------------------------------
+# EvalUtil (util/eval_tool.py:5-122) restated in numpy with the reference's dtypes  -- SURVEY.md section 8 f.1
+# --------------------------------------------------------------------------------------
+def eval_feed_np(jt_uvd_pred, jt_xyz_gt, center_xyz, M, cube, img_size, paras=NYU_PARAS, flip=NYU_FLIP, return_xyz=False):
+    """One sample (eval_tool.py:20-50).  Returns (jt_uvd_img (J,3) f32, euclidean_dist (J,) f32, diff_mean (3,) f32)."""
+    import numpy as np
+    uvd = np.array(jt_uvd_pred, dtype=np.float32).copy()
+    gt = np.asarray(jt_xyz_gt, dtype=np.float32)
+    center_xyz, M, cube = (np.asarray(t, dtype=np.float32) for t in (center_xyz, M, cube))
+    M_inv = np.linalg.inv(M)                                                    # :33
+    uvd[:, :2] = (uvd[:, :2] + 1) * img_size / 2.                               # :38
+    uvd[:, 2] = uvd[:, 2] * cube[2] / 2. + center_xyz[2]                        # :39
+    trans = np.hstack([uvd[:, :2], np.ones((uvd.shape[0], 1))])                 # :40 (float64)
+    uvd[:, :2] = np.dot(M_inv, trans.T).T[:, :2]                                # :41
+    xyz = uvd.copy()                                                            # util.py:15-19
+    xyz[:, :2] = (xyz[:, :2] - paras[2:]) * xyz[:, 2:] / paras[:2]
+    xyz[:, 1] *= flip
+    gt_mm = gt * (cube / 2.) + center_xyz                                       # :45
+    diff = gt_mm - xyz                                                          # :48
+    if return_xyz:
+        return xyz
+    return uvd, np.sqrt(np.sum(np.square(diff), axis=1)), diff.mean(axis=0)     # :49-50
+
+
+def eval_measures_np(dist, vis=None):
+    """get_measures (eval_tool.py:80-122) over dist (N,J) float32 [with optional (N,J) visibility]."""
+    import numpy as np
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    thresholds = np.linspace(0, 50, 100)
+    norm_factor = trapz(np.ones_like(thresholds), thresholds)
+    means, medians, aucs, curves = [], [], [], []
+    for j in range(dist.shape[1]):
+        data = np.array([dist[n, j] for n in range(dist.shape[0]) if vis is None or vis[n, j]])
+        if len(data) == 0:
+            continue
+        means.append(np.mean(data)); medians.append(np.median(data))
+        curve = np.array([np.mean((data <= t).astype('float')) for t in thresholds])
+        curves.append(curve)
+        aucs.append(trapz(curve, thresholds) / norm_factor)
+    return np.mean(np.array(means)), np.mean(np.array(medians)), np.mean(np.array(aucs)), np.mean(np.array(curves), 0), thresholds
+
+
+def eval_case_inputs(N: int, J: int, seed: int, img_size: int = 128):
+    """Synthetic EvalUtil inputs: crop affines built like Loader.center2transmat (loader.py:210-240) with an in-plane rotation as the
+    augmentation adds, hand centres around 760 mm, NYU cubes (300 mm, and 250 mm as for the second test subject, nyu_loader.py:32-33)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    uvd = rng.uniform(-0.8, 0.8, (N, J, 3)).astype(np.float32)
+    center = (np.array([0., 0., 760.]) + rng.normal(0, 40, (N, 3))).astype(np.float32)
+    cube = np.where(rng.rand(N, 1) < 0.5, 300.0, 250.0).repeat(3, 1).astype(np.float32)
+    Ms = []
+    for n in range(N):
+        s = img_size / rng.uniform(150, 260)
+        th = rng.uniform(-0.6, 0.6) if n % 2 else 0.0
+        t1 = np.eye(3); t1[0, 2], t1[1, 2] = -rng.uniform(150, 330), -rng.uniform(80, 250)
+        sc = np.diag([s, s, 1.0])
+        rot = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+        t2 = np.eye(3); t2[0, 2], t2[1, 2] = rng.randint(0, 12), rng.randint(0, 12)
+        Ms.append((t2 @ rot @ sc @ t1).astype(np.float32))
+    # ground truth = the prediction's own camera-space position + N(0, 9 mm) per axis (a few joints 60 mm off), cube-normalised as the
+    # loader does (nyu_loader.py:64): errors then spread over the 0-50 mm PCK thresholds
+    gt = np.zeros_like(uvd)
+    for n in range(N):
+        xyz = eval_feed_np(uvd[n], np.zeros((J, 3), np.float32), center[n], Ms[n], cube[n], img_size, return_xyz=True)
+        noise = rng.normal(0, 9.0, (J, 3)) + (rng.rand(J, 1) < 0.05) * 60.0
+        gt[n] = ((xyz + noise - center[n]) / (cube[n] / 2.)).astype(np.float32)
+    vis = rng.rand(N, J) > 0.15
+    return uvd, gt, center, np.stack(Ms), cube, vis
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8 d)
 # --------------------------------------------------------------------------------------
 def synthetic_batch(B: int, H: int, J: int, seed: int) -> Tuple[Tensor, Tensor]:

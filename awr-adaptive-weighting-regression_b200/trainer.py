@@ -213,6 +213,11 @@ class FusedTrainer:
         pp = self._pipe
         return self.collect() if pp["submitted"] - pp["collected"] == 2 else None
 
+    def feed_eval(self, eval_tool, jt_xyz_gt, center_xyz, M, cube):
+        """train.py:141-148 without the per-frame `.cpu()` copies: hands the step's predicted UVD (still on the device) and the batch's
+        ground truth / crop geometry to awr_b200.EvalUtil.feed_batch.  Enqueue it right after the step; no host synchronisation."""
+        eval_tool.feed_batch(self.uvd, jt_xyz_gt, center_xyz, M, cube)
+
     def broadcast_parameters(self, src=0):
         """DDP-style start: every replica takes rank `src`'s parameters and BN buffers."""
         if self.world > 1:

@@ -120,5 +120,5 @@ def test_lagged_pipeline_matches_blocking_steps():
     for k, ((a0, a1), (b0, b1)) in enumerate(zip(*results)):
         tol = 1e-3
         assert abs(a0 - b0) <= tol * abs(a0) + 1e-9 and abs(a1 - b1) <= tol * abs(a1) + 1e-9, (k, results)
-    coord = [r[0] for r in results[0]]
-    assert max(coord) > 2.0 * min(coord)        # the batches really are distinguishable by their losses
+    coord = sorted(r[0] for r in results[0])
+    assert all(b > 1.01 * a for a, b in zip(coord, coord[1:]))        # the batches are distinguishable by their losses (>= 1 % apart, tolerance 0.1 %)

@@ -420,9 +420,9 @@ def main():
         hms = head_pair_time(tr)
         hach = hb / (hms * 1e-3) / 1e9
         roof_head = {"kernel": "fused AWR head+loss (head_fwd_kernel + head_bwd_kernel)", "bound": "hbm", "achieved": round(hach, 1), "peak": pk["hbm"],
-                     "unit": "GB/s", "frac": round(hach / pk["hbm"], 4), "traffic": 61054976, "peak_source": pk["src"] + " (copy)",
+                     "unit": "GB/s", "frac": round(hach / pk["hbm"], 4), "traffic": 61189632, "peak_source": pk["src"] + " (copy)",
                      "pair_us": round(1e3 * hms, 2), "bytes_per_step": hb, "how": "cold L2 (512 MB fill before each fwd+bwd pair), 8 repetitions; "
-                     "traffic = ncu dram bytes of the pair (profiles/r01_final_head_full.md)"}
+                     "traffic = ncu dram bytes of the pair (profiles/r01_final2_head_full.md)"}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------------
     cpu = None

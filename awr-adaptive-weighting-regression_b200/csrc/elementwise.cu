@@ -71,14 +71,22 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads) channel_stats_kernel(const T* __restrict__ x, long long M, int C, float* __restrict__ sums, int with_sq) {
   pdl_entry();
   __shared__ float smem[kEwThreads * 8];
+  constexpr int U = 4;                        // four 16-byte loads in flight per thread (see Raw8)
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
   float acc[2][8] = {};
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
-    float v[8];
-    Vec8<T>::load(x + i * 8, v);
+  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < items; i0 += U * stride) {
+    Raw8<T> r[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { acc[0][k] += v[k]; acc[1][k] += v[k] * v[k]; }
+    for (int u = 0; u < U; ++u) if (i0 + u * stride < items) r[u].load(x + (i0 + u * stride) * 8);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * stride >= items) break;
+      float v[8];
+      r[u].unpack(v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { acc[0][k] += v[k]; acc[1][k] += v[k] * v[k]; }
+    }
   }
   if (with_sq) block_channel_reduce<2>(acc, G, C, sums, smem);
   else {
@@ -126,34 +134,45 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, 
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
-affine_act_kernel(const T* __restrict__ y, const float* __restrict__ ss, const T* __restrict__ res, const float* __restrict__ res_ss,
-                  T* __restrict__ out, long long M, int C, int relu) {
+affine_act_kernel(const T* y, const float* __restrict__ ss, const T* res, const float* __restrict__ res_ss, T* out, long long M, int C, int relu) {
   pdl_entry();
+  constexpr int U = 4;                        // `out` may alias `y` (in-place accumulate): items are thread-private, loads precede stores
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
-    const int c0 = (int)(i % G) * 8;
-    float v[8];
-    Vec8<T>::load(y + i * 8, v);
-    if (ss) {
+  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < items; i0 += U * stride) {
+    Raw8<T> ry[U], rr[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = v[k] * __ldg(ss + c0 + k) + __ldg(ss + C + c0 + k);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < items) { ry[u].load(y + i * 8); if (res) rr[u].load(res + i * 8); }
     }
-    if (res) {
-      float r[8];
-      Vec8<T>::load(res + i * 8, r);
-      if (res_ss) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = r[k] * __ldg(res_ss + c0 + k) + __ldg(res_ss + C + c0 + k);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= items) break;
+      const int c0 = (int)(i % G) * 8;
+      float v[8];
+      ry[u].unpack(v);
+      if (ss) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = v[k] * __ldg(ss + c0 + k) + __ldg(ss + C + c0 + k);
       }
+      if (res) {
+        float r[8];
+        rr[u].unpack(r);
+        if (res_ss) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += r[k];
-    }
-    if (relu) {
+          for (int k = 0; k < 8; ++k) r[k] = r[k] * __ldg(res_ss + c0 + k) + __ldg(res_ss + C + c0 + k);
+        }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        for (int k = 0; k < 8; ++k) v[k] += r[k];
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+      Vec8<T>::store(out + i * 8, v);
     }
-    Vec8<T>::store(out + i * 8, v);
   }
 }
 
@@ -956,25 +975,41 @@ bn_bwd_fused_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
 // relu backward / plain masked copy: dx = dout * (act_out > 0)  (+ add into existing dx when accumulate)
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
-relu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ addend, T* __restrict__ dx, long long n8) {
+relu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* addend, T* dx, long long n8) {
   pdl_entry();
+  constexpr int U = 4;                        // `dx` may alias `addend` (accumulate): items are thread-private, loads precede stores
   const long long stride = (long long)gridDim.x * kEwThreads;
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n8; i += stride) {
-    float g[8];
-    Vec8<T>::load(dout + i * 8, g);
-    if (act_out) {
-      float a[8];
-      Vec8<T>::load(act_out + i * 8, a);
+  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < n8; i0 += U * stride) {
+    Raw8<T> rg[U], ra[U], rb[U];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n8) {
+        rg[u].load(dout + i * 8);
+        if (act_out) ra[u].load(act_out + i * 8);
+        if (addend) rb[u].load(addend + i * 8);
+      }
     }
-    if (addend) {
-      float b[8];
-      Vec8<T>::load(addend + i * 8, b);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] += b[k];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n8) break;
+      float g[8];
+      rg[u].unpack(g);
+      if (act_out) {
+        float a[8];
+        ra[u].unpack(a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
+      }
+      if (addend) {
+        float b[8];
+        rb[u].unpack(b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] += b[k];
+      }
+      Vec8<T>::store(dx + i * 8, g);
     }
-    Vec8<T>::store(dx + i * 8, g);
   }
 }
 
@@ -1017,6 +1052,87 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, unsigned char* 
       pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((unsigned)bi[3] << 24);
       pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((unsigned)bi[7] << 24);
       *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
+  }
+}
+
+// MaxPool2d(2,2) (hourglass.py:68,115; H, W even): the four taps of an output pixel are loaded before the first comparison
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, unsigned char* __restrict__ idx, int N, int H, int W, int C) {
+  pdl_entry();
+  const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int cg = (int)(i % G);
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const T* base = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cg * 8;
+    Raw8<T> r[4];
+    r[0].load(base); r[1].load(base + C); r[2].load(base + (long long)W * C); r[3].load(base + (long long)W * C + C);
+    float best[8];
+    unsigned bi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { best[q] = -INFINITY; bi[q] = 0u; }
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      float v[8];
+      r[tap].unpack(v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (v[q] > best[q]) { best[q] = v[q]; bi[q] = (unsigned)tap; }
+    }
+    Vec8<T>::store(out + i * 8, best);
+    if (idx) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
+  }
+}
+
+// its backward: windows do not overlap, so a thread owns one window (x 8 channels): one load of the pooled gradient + arg-max bytes,
+// four stores (the gradient at the arg-max pixel, zero elsewhere; read-modify-write when accumulating)
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+maxpool2_bwd_kernel(const T* __restrict__ dout, const unsigned char* __restrict__ idx, T* dx, int N, int H, int W, int C, int accumulate) {
+  pdl_entry();
+  const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int cg = (int)(i % G);
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    T* base = dx + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + cg * 8;
+    const long long off[4] = {0, C, (long long)W * C, (long long)W * C + C};
+    Raw8<T> rg, ro[4];
+    rg.load(dout + i * 8);
+    const uint2 pk = *reinterpret_cast<const uint2*>(idx + i * 8);
+    if (accumulate) {
+#pragma unroll
+      for (int tap = 0; tap < 4; ++tap) ro[tap].load(base + off[tap]);
+    }
+    float g[8];
+    rg.unpack(g);
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      float o[8];
+      if (accumulate) ro[tap].unpack(o);
+      else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const unsigned b = (q < 4) ? ((pk.x >> (8 * q)) & 0xffu) : ((pk.y >> (8 * (q - 4))) & 0xffu);
+        if (b == (unsigned)tap) o[q] += g[q];
+      }
+      Vec8<T>::store(base + off[tap], o);
     }
   }
 }
@@ -1250,7 +1366,7 @@ extern "C" {
 
 int awr_channel_stats(const void* x, int dtype, long long M, int C, float* sums, int with_sq, void* stream) {
   AWR_HOST_CHECK(x && sums && M > 0 && chan_ok(C));
-  DISPATCH_T(dtype, launch_pdl(channel_stats_kernel<T>, dim3(red_blocks(M, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)x, M, C, sums, with_sq));
+  DISPATCH_T(dtype, launch_pdl(channel_stats_kernel<T>, dim3(ew_grid(M * (C / 8), 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)x, M, C, sums, with_sq));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -1333,7 +1449,7 @@ int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float*
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream) {
   AWR_HOST_CHECK(y && out && M > 0 && C % 8 == 0);
-  DISPATCH_T(dtype, launch_pdl(affine_act_kernel<T>, dim3(ew_blocks(M * (C / 8))), dim3(kEwThreads), 0, (cudaStream_t)stream, 
+  DISPATCH_T(dtype, launch_pdl(affine_act_kernel<T>, dim3(ew_grid(M * (C / 8), 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M, C, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1412,7 +1528,7 @@ int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const
 
 int awr_relu_bwd(const void* dout, const void* act_out, const void* addend, void* dx, int dtype, long long n, void* stream) {
   AWR_HOST_CHECK(dout && dx && n > 0 && n % 8 == 0);
-  DISPATCH_T(dtype, launch_pdl(relu_bwd_kernel<T>, dim3(ew_blocks(n / 8)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)dout, (const T*)act_out,
+  DISPATCH_T(dtype, launch_pdl(relu_bwd_kernel<T>, dim3(ew_grid(n / 8, 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)dout, (const T*)act_out,
                                                                                                  (const T*)addend, (T*)dx, n / 8));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1422,6 +1538,12 @@ int awr_maxpool_fwd(const void* x, void* out, unsigned char* idx, int dtype, int
                     void* stream) {
   AWR_HOST_CHECK(x && out && N > 0 && C % 8 == 0 && k >= 1 && k <= 3 && s >= 1);
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  if (k == 2 && s == 2 && p == 0 && H % 2 == 0 && W % 2 == 0) {
+    DISPATCH_T(dtype, launch_pdl(maxpool2_fwd_kernel<T>, dim3(ew_grid((long long)N * Ho * Wo * (C / 8), 1)), dim3(kEwThreads), 0, (cudaStream_t)stream,
+                                 (const T*)x, (T*)out, idx, N, H, W, C));
+    AWR_LAUNCH_CHECK();
+    return AWR_OK;
+  }
   DISPATCH_T(dtype, launch_pdl(maxpool_fwd_kernel<T>, dim3(ew_blocks((long long)N * Ho * Wo * (C / 8), 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)x, (T*)out, idx, N, H, W, C, Ho, Wo, k, s, p));
   AWR_LAUNCH_CHECK();
@@ -1432,6 +1554,12 @@ int awr_maxpool_bwd(const void* dout, const unsigned char* idx, void* dx, int dt
                     int accumulate, void* stream) {
   AWR_HOST_CHECK(dout && idx && dx && N > 0 && C % 8 == 0);
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
+  if (k == 2 && s == 2 && p == 0 && H % 2 == 0 && W % 2 == 0) {
+    DISPATCH_T(dtype, launch_pdl(maxpool2_bwd_kernel<T>, dim3(ew_grid((long long)N * Ho * Wo * (C / 8), 1)), dim3(kEwThreads), 0, (cudaStream_t)stream,
+                                 (const T*)dout, idx, (T*)dx, N, H, W, C, accumulate));
+    AWR_LAUNCH_CHECK();
+    return AWR_OK;
+  }
   DISPATCH_T(dtype, launch_pdl(maxpool_bwd_kernel<T>, dim3(ew_blocks((long long)N * H * W * (C / 8), 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)dout, idx, (T*)dx, N, H, W, C, Ho, Wo, k, s, p, accumulate));
   AWR_LAUNCH_CHECK();

@@ -134,45 +134,34 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, 
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
-affine_act_kernel(const T* y, const float* __restrict__ ss, const T* res, const float* __restrict__ res_ss, T* out, long long M, int C, int relu) {
+affine_act_kernel(const T* __restrict__ y, const float* __restrict__ ss, const T* __restrict__ res, const float* __restrict__ res_ss,
+                  T* __restrict__ out, long long M, int C, int relu) {
   pdl_entry();
-  constexpr int U = 4;                        // `out` may alias `y` (in-place accumulate): items are thread-private, loads precede stores
   const int G = C >> 3;
   const long long items = M * G, stride = (long long)gridDim.x * kEwThreads;
-  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < items; i0 += U * stride) {
-    Raw8<T> ry[U], rr[U];
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
+    const int c0 = (int)(i % G) * 8;
+    float v[8];
+    Vec8<T>::load(y + i * 8, v);
+    if (ss) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < items) { ry[u].load(y + i * 8); if (res) rr[u].load(res + i * 8); }
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * __ldg(ss + c0 + k) + __ldg(ss + C + c0 + k);
     }
+    if (res) {
+      float r[8];
+      Vec8<T>::load(res + i * 8, r);
+      if (res_ss) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i >= items) break;
-      const int c0 = (int)(i % G) * 8;
-      float v[8];
-      ry[u].unpack(v);
-      if (ss) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = v[k] * __ldg(ss + c0 + k) + __ldg(ss + C + c0 + k);
+        for (int k = 0; k < 8; ++k) r[k] = r[k] * __ldg(res_ss + c0 + k) + __ldg(res_ss + C + c0 + k);
       }
-      if (res) {
-        float r[8];
-        rr[u].unpack(r);
-        if (res_ss) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) r[k] = r[k] * __ldg(res_ss + c0 + k) + __ldg(res_ss + C + c0 + k);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] += r[k];
-      }
-      if (relu) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-      }
-      Vec8<T>::store(out + i * 8, v);
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
     }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    Vec8<T>::store(out + i * 8, v);
   }
 }
 
@@ -975,41 +964,25 @@ bn_bwd_fused_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
 // relu backward / plain masked copy: dx = dout * (act_out > 0)  (+ add into existing dx when accumulate)
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
-relu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* addend, T* dx, long long n8) {
+relu_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ addend, T* __restrict__ dx, long long n8) {
   pdl_entry();
-  constexpr int U = 4;                        // `dx` may alias `addend` (accumulate): items are thread-private, loads precede stores
   const long long stride = (long long)gridDim.x * kEwThreads;
-  for (long long i0 = (long long)blockIdx.x * kEwThreads + threadIdx.x; i0 < n8; i0 += U * stride) {
-    Raw8<T> rg[U], ra[U], rb[U];
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n8; i += stride) {
+    float g[8];
+    Vec8<T>::load(dout + i * 8, g);
+    if (act_out) {
+      float a[8];
+      Vec8<T>::load(act_out + i * 8, a);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < n8) {
-        rg[u].load(dout + i * 8);
-        if (act_out) ra[u].load(act_out + i * 8);
-        if (addend) rb[u].load(addend + i * 8);
-      }
+      for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
     }
+    if (addend) {
+      float b[8];
+      Vec8<T>::load(addend + i * 8, b);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i >= n8) break;
-      float g[8];
-      rg[u].unpack(g);
-      if (act_out) {
-        float a[8];
-        ra[u].unpack(a);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] = (a[k] > 0.f) ? g[k] : 0.f;
-      }
-      if (addend) {
-        float b[8];
-        rb[u].unpack(b);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g[k] += b[k];
-      }
-      Vec8<T>::store(dx + i * 8, g);
+      for (int k = 0; k < 8; ++k) g[k] += b[k];
     }
+    Vec8<T>::store(dx + i * 8, g);
   }
 }
 
@@ -1449,7 +1422,7 @@ int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float*
 int awr_affine_act(const void* y, const float* scale_shift, const void* res, const float* res_scale_shift, void* out, int dtype,
                    long long M, int C, int relu, void* stream) {
   AWR_HOST_CHECK(y && out && M > 0 && C % 8 == 0);
-  DISPATCH_T(dtype, launch_pdl(affine_act_kernel<T>, dim3(ew_grid(M * (C / 8), 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
+  DISPATCH_T(dtype, launch_pdl(affine_act_kernel<T>, dim3(ew_blocks(M * (C / 8))), dim3(kEwThreads), 0, (cudaStream_t)stream, 
                         (const T*)y, scale_shift, (const T*)res, res_scale_shift, (T*)out, M, C, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1528,7 +1501,7 @@ int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const
 
 int awr_relu_bwd(const void* dout, const void* act_out, const void* addend, void* dx, int dtype, long long n, void* stream) {
   AWR_HOST_CHECK(dout && dx && n > 0 && n % 8 == 0);
-  DISPATCH_T(dtype, launch_pdl(relu_bwd_kernel<T>, dim3(ew_grid(n / 8, 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)dout, (const T*)act_out,
+  DISPATCH_T(dtype, launch_pdl(relu_bwd_kernel<T>, dim3(ew_blocks(n / 8)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)dout, (const T*)act_out,
                                                                                                  (const T*)addend, (T*)dx, n / 8));
   AWR_LAUNCH_CHECK();
   return AWR_OK;

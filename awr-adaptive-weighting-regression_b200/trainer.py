@@ -23,7 +23,9 @@ from .modules import AWRBackbone
 
 class FusedTrainer:
     def __init__(self, module: AWRBackbone, batch_size, img_size, kernel_size, coord_weight=1.0, dense_weight=1.0, lr=1e-3,
-                 betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1, use_graph=True, process_group=None):
+                 betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1, use_graph=True, process_group=None, all_stacks=False):
+        """all_stacks (hourglass_N, N > 1): supervise every stack and sum the per-stack losses (test.py:74-80); the default keeps
+        train.py:116-121's behaviour, where only the last stack's loss survives the loop."""
         if not isinstance(module, AWRBackbone):
             raise TypeError("FusedTrainer drives awr_b200 backbones (get_deconv_net / PoseNet)")
         self.module = module
@@ -39,6 +41,7 @@ class FusedTrainer:
         self.lib = L.lib()
         J = module._J
         self.J = J
+        self.sup_heads = list(self.plan.heads) if all_stacks else [self.plan.heads[-1]]
         self.head = self.plan.heads[-1]
         self.F = self.head.pred.shape[-1]
         n = self.store.params.numel()
@@ -46,10 +49,12 @@ class FusedTrainer:
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.jt = torch.empty(self.B, J, 3, dtype=torch.float32, device=dev)
-        self.uvd = torch.empty(self.B, J, 3, dtype=torch.float32, device=dev)
-        self.loss = torch.zeros(2, dtype=torch.float32, device=dev)
-        self.ws = torch.zeros(4 * self.B * J + 4, dtype=torch.float32, device=dev)
-        self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        ns = len(self.sup_heads)
+        self.uvd_all = [torch.empty(self.B, J, 3, dtype=torch.float32, device=dev) for _ in range(ns)]
+        self.loss_all = torch.zeros(ns, 2, dtype=torch.float32, device=dev)       # per supervised stack: (SmoothL1 joints, SmoothL1 dense)
+        self.ws_all = [torch.zeros(4 * self.B * J + 4, dtype=torch.float32, device=dev) for _ in range(ns)]
+        self.uvd, self.loss, self.ws = self.uvd_all[-1], self.loss_all[-1], self.ws_all[-1]        # the last stack (what test.py evaluates)
+        self.loss_host = torch.zeros(ns, 2, dtype=torch.float32).pin_memory()
         self.steps_done = 0
         self.use_graph = use_graph
         self.graph_fb = self.graph_opt = None
@@ -58,7 +63,7 @@ class FusedTrainer:
         if self.plan.precision == "bf16":
             self.store.refresh_shadow()
         # launches of OUR kernels per step (memsets / NCCL not counted)
-        self.launches_per_step = len(self.plan.fwd) + len(self.plan.bwd) + 2 + 2
+        self.launches_per_step = len(self.plan.fwd) + len(self.plan.bwd) + 2 * ns + 2
 
     # ---- launch sequences -------------------------------------------------------------------------------
     def _fwd_bwd(self, part=None):
@@ -69,15 +74,17 @@ class FusedTrainer:
             return
         pl.arena_used().zero_()
         st.grads.zero_()
-        for h in pl.heads[:-1]:
-            h.dpred.zero_()
+        for h in pl.heads:
+            if h not in self.sup_heads:
+                h.dpred.zero_()
         pl.run_forward(s)
-        hd = self.head
-        L.check(self.lib.awr_head_fwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), self.uvd.data_ptr(),
-                                      self.loss.data_ptr(), self.ws.data_ptr(), self.B, self.J, self.F, self.H, self.ks, s), "awr_head_fwd")
-        L.check(self.lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), self.uvd.data_ptr(),
-                                      self.ws.data_ptr(), None, None, hd.dpred.data_ptr(), self.B, self.J, self.F, self.H, self.ks,
-                                      self.cw, self.dw, s), "awr_head_bwd")
+        for i, hd in enumerate(self.sup_heads):
+            uvd, ws, loss = self.uvd_all[i], self.ws_all[i], self.loss_all[i]
+            L.check(self.lib.awr_head_fwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), uvd.data_ptr(),
+                                          loss.data_ptr(), ws.data_ptr(), self.B, self.J, self.F, self.H, self.ks, s), "awr_head_fwd")
+            L.check(self.lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), uvd.data_ptr(),
+                                          ws.data_ptr(), None, None, hd.dpred.data_ptr(), self.B, self.J, self.F, self.H, self.ks,
+                                          self.cw, self.dw, s), "awr_head_bwd")
         pl.run_backward(s, side=self.side, part=part)
 
     def _opt(self):
@@ -157,9 +164,9 @@ class FusedTrainer:
         Includes the H2D copies and the D2H loss read-back (train.py:109-133)."""
         self.load_batch(img, jt_uvd_gt)
         self.run_step()
-        self.loss_host.copy_(self.loss, non_blocking=True)
+        self.loss_host.copy_(self.loss_all, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return float(self.loss_host[0]), float(self.loss_host[1])
+        return float(self.loss_host[:, 0].sum()), float(self.loss_host[:, 1].sum())       # sums over the supervised stacks
 
     # ---- pipelined form of train_step: the host never waits for the step it has just enqueued -------------------------------
     def submit(self, img, jt_uvd_gt):
@@ -174,7 +181,7 @@ class FusedTrainer:
                 "jt": [torch.empty(B, J, 3, dtype=torch.float32, device=dev) for _ in range(2)],
                 "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)],
                 "done": [torch.cuda.Event() for _ in range(2)],
-                "loss": [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)],
+                "loss": [torch.zeros(len(self.sup_heads), 2, dtype=torch.float32).pin_memory() for _ in range(2)],
                 "submitted": 0, "collected": 0}
         pp = self._pipe
         if pp["submitted"] - pp["collected"] >= 2:
@@ -191,7 +198,7 @@ class FusedTrainer:
         self.jt.copy_(pp["jt"][slot], non_blocking=True)
         pp["free"][slot].record(main)
         self.run_step()
-        pp["loss"][slot].copy_(self.loss, non_blocking=True)
+        pp["loss"][slot].copy_(self.loss_all, non_blocking=True)
         pp["done"][slot].record(main)
         pp["submitted"] += 1
 
@@ -203,7 +210,7 @@ class FusedTrainer:
         slot = pp["collected"] % 2
         pp["done"][slot].synchronize()
         pp["collected"] += 1
-        return float(pp["loss"][slot][0]), float(pp["loss"][slot][1])
+        return float(pp["loss"][slot][:, 0].sum()), float(pp["loss"][slot][:, 1].sum())
 
     def train_step_lagged(self, img, jt_uvd_gt):
         """train_step with one step of lag on the logged losses: enqueues this batch and returns the losses of the PREVIOUS call (None on
@@ -224,6 +231,35 @@ class FusedTrainer:
             dp.broadcast_([self.store.params] + list(self.store.buffers.values()), src, self.pg)
             if self.plan.precision == "bf16":
                 self.store.refresh_shadow()
+
+    def set_lr(self, lr):
+        """Learning-rate schedules (train.py:68-69 StepLR / ReduceLROnPlateau drive `optimizer.param_groups[0]['lr']`): the rate is a
+        launch argument of the captured Adam graph, so a change re-captures that two-kernel graph; the forward/backward graph is untouched."""
+        lr = float(lr)
+        if lr == self.lr:
+            return
+        self.lr = lr
+        if self.graph_opt is not None:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self._opt()
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of optimizer_state_dict(): resume from the `optimizer` entry of a checkpoint (train.py:89-96), i.e. a torch.optim.Adam
+        state over the canonical parameter order.  Parameters the reference never steps (unused Hourglass skip layers) may be absent."""
+        lay = self.store.layout
+        self.m.zero_(); self.v.zero_()
+        steps = 0
+        for i, name in enumerate(self.module._pnames):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            lay.view(self.m, name).copy_(st["exp_avg"].to(self.device))
+            lay.view(self.v, name).copy_(st["exp_avg_sq"].to(self.device))
+            steps = max(steps, int(float(st["step"])))
+        self.steps_done = steps
+        self.step_dev.fill_(float(steps))
+        self.set_lr(sd["param_groups"][0]["lr"])
 
     def optimizer_state_dict(self):
         """torch.optim.Adam-shaped state (train.py:165-172 saves optimizer.state_dict()) over the canonical parameters."""

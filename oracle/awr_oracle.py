@@ -370,9 +370,29 @@ def backbone_forward(sd, x, net: str, downsample: int, training: bool, new_stats
 
 
 def loss_and_grads(sd: Dict[str, Tensor], img: Tensor, jt_uvd_gt: Tensor, net: str, downsample: int,
-                   kernel_size: float, coord_weight: float, dense_weight: float):
+                   kernel_size: float, coord_weight: float, dense_weight: float, all_stacks: bool = False):
     """Forward + backward of one train.py iteration (train-mode BN).  Returns
-    (loss, loss_coord, loss_dense, uvd_pred, offset_pred, grads{name: tensor}, new_stats)."""
+    (loss, loss_coord, loss_dense, uvd_pred, offset_pred, grads{name: tensor}, new_stats).
+    all_stacks (hourglass_N only): supervise every stack and SUM the per-stack losses, the accumulation test.py:74-80 performs
+    (`loss += loss_coord + loss_offset`); train.py:116-121 overwrites `loss` in that loop, so the default keeps the last stack only.
+    loss_coord / loss_dense are then the sums over stacks, uvd_pred / offset_pred those of the last stack."""
+    if all_stacks and net.startswith("hourglass"):
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
+                  and not k.endswith(("running_mean", "running_var"))}
+        full = dict(sd); full.update(params)
+        new_stats = {}
+        Fs = img.shape[-1] // downsample
+        offset_gt = joint2offset(jt_uvd_gt, img, kernel_size, Fs)
+        preds = hourglass_forward(full, img, int(net.split("_")[1]), True, new_stats)
+        l_coord = l_dense = 0.0
+        for pred in preds:
+            uvd = offset2joint_softmax(pred, img, kernel_size)
+            l_coord = l_coord + smooth_l1(uvd, jt_uvd_gt)
+            l_dense = l_dense + smooth_l1(pred, offset_gt)
+        loss = coord_weight * l_coord + dense_weight * l_dense
+        loss.backward()
+        grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
+        return loss.detach(), l_coord.detach(), l_dense.detach(), uvd.detach(), pred.detach(), grads, new_stats
     params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
               and not k.endswith(("running_mean", "running_var"))}
     full = dict(sd); full.update(params)

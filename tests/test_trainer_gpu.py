@@ -122,3 +122,63 @@ def test_lagged_pipeline_matches_blocking_steps():
         assert abs(a0 - b0) <= tol * abs(a0) + 1e-9 and abs(a1 - b1) <= tol * abs(a1) + 1e-9, (k, results)
     coord = sorted(r[0] for r in results[0])
     assert all(b > 1.01 * a for a, b in zip(coord, coord[1:]))        # the batches are distinguishable by their losses (>= 1 % apart, tolerance 0.1 %)
+
+
+def test_all_stacks_supervision_vs_oracle():
+    """hourglass_2 with every stack supervised and the per-stack losses summed (test.py:74-80) vs the oracle's all_stacks step."""
+    import awr_b200
+    from awr_b200.trainer import FusedTrainer
+    B, H, J, ds, ks, net = 2, 128, 14, 2, 0.4, "hourglass_2"
+    sd = O.randomize_bn(O.hourglass_init(2, J, 51, head_gain=1.0), 52)
+    m = awr_b200.PoseNet(net, J, precision="fp32")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    img, jt = O.synthetic_batch(B, H, J, 53)
+    loss, lc, ld, uvd, pred, grads, _ = O.loss_and_grads(sd, img, jt, net, ds, ks, 0.7, 1.3, all_stacks=True)
+    last = O.loss_and_grads(sd, img, jt, net, ds, ks, 0.7, 1.3)
+    assert lc.item() > 1.5 * last[1].item()                                  # two stacks really contribute
+    tr = FusedTrainer(m, B, H, ks, 0.7, 1.3, lr=1e-3, use_graph=False, all_stacks=True)
+    assert len(tr.sup_heads) == 2
+    l0, l1 = tr.train_step(img.cuda(), jt.cuda())
+    assert abs(l0 - lc.item()) < 2e-3 * abs(lc.item()) and abs(l1 - ld.item()) < 2e-3 * abs(ld.item())
+    assert (tr.uvd.cpu() - uvd).abs().max().item() < 1e-3
+    lay, bad = tr.store.layout, []
+    for k, g in grads.items():
+        if g is None or g.abs().mean().item() < 1e-7:
+            continue
+        got = lay.view(tr.store.grads, k).cpu()
+        rel = (got - g).norm().item() / g.norm().item()
+        if rel > 3e-2:
+            bad.append((k, rel))
+    assert not bad, bad[:10]
+
+
+def test_set_lr_and_optimizer_state_roundtrip():
+    import awr_b200
+    from awr_b200.trainer import FusedTrainer
+    B, H, J, ds = 2, 128, 14, 2
+    sd = O.randomize_bn(O.resnet_deconv_init(18, J, ds, 61, head_std=0.02), 62)
+    img, jt = (t.cuda() for t in O.synthetic_batch(B, H, J, 63))
+
+    def make():
+        m = awr_b200.get_deconv_net(18, J, ds, precision="fp32")
+        m.load_state_dict(sd, strict=True)
+        return m.cuda()
+    m = make()
+    tr = FusedTrainer(m, B, H, 1.0, 1.0, 1.0, lr=1e-3, use_graph=True)
+    tr.train_step(img, jt)
+    p1 = tr.store.params.clone()
+    tr.set_lr(0.0)                                                            # re-captures the Adam graph only
+    tr.train_step(img, jt)
+    assert torch.equal(tr.store.params, p1) and tr.step_dev.item() == 2.0    # zero rate: moments advance, parameters do not
+    tr.set_lr(1e-4)
+    tr.train_step(img, jt)
+    d = (tr.store.params - p1).abs().max().item()
+    assert 0.0 < d <= 1.2e-4                                                  # Adam moves a parameter by at most ~lr per step
+    od = tr.optimizer_state_dict()
+    m2 = make()
+    m2.load_state_dict(m.state_dict(), strict=True)
+    tr2 = FusedTrainer(m2, B, H, 1.0, 1.0, 1.0, lr=1e-3, use_graph=True)
+    tr2.load_optimizer_state_dict(od)
+    assert tr2.lr == 1e-4 and tr2.steps_done == 3 and tr2.step_dev.item() == 3.0
+    assert torch.equal(tr2.m, tr.m) and torch.equal(tr2.v, tr.v)

@@ -72,6 +72,14 @@ int awr_eval_feed(const float* uvd_pred, const float* xyz_gt_norm, const float* 
 int awr_eval_measures(const float* dist, long long N, int J, int nthr, float thr_max, double* sum, unsigned* count, unsigned* pck_count,
                       void* stream);
 
+/* ---- depth preprocessing (dataloader/loader.py:19-51,88-101,190-207; nyu_loader.py:71-74) -------------------------- */
+
+/* Loader.crop + Loader.normalize of the non-augmented path for N raw frames: src (N,Hs,Ws) float32 millimetres (src_format 0) or
+ * (N,Hs,Ws,3) uint8 BGR with depth = B + 256*G (src_format 1); params (N,12) doubles = crop-box geometry computed on the host
+ * (layout in csrc/preprocess.cu, built by awr_b200/preprocess.py); out (N,1,img_size,img_size) float32 in [-1,1], background +1. */
+int awr_crop_normalize(const void* src, int src_format, int N, int Hs, int Ws, const double* params, int img_size, float* out,
+                       void* stream);
+
 /* ---- NHWC elementwise / normalisation kernels (storage dtype: AWR_DTYPE_F32 or AWR_DTYPE_BF16) ---------------
  * Internal activation layout is NHWC (M = N*H*W pixels x C channels, C a power of two in [64,2048] for the
  * per-channel reductions).  These replace nn.BatchNorm2d / nn.ReLU / residual adds / nn.MaxPool2d / nn.Upsample

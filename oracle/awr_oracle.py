@@ -520,6 +520,91 @@ def eval_case_inputs(N: int, J: int, seed: int, img_size: int = 128):
 
 
 # --------------------------------------------------------------------------------------
+# depth preprocessing of the non-augmented path (dataloader/loader.py:19-51,88-101,181-240; nyu_loader.py:38-60)  -- SURVEY 8 f.2
+# --------------------------------------------------------------------------------------
+def center2bounds_np(center, csize, paras=NYU_PARAS):
+    """loader.py:181-188 (float64 arithmetic on a float32 centre, int() truncation)."""
+    import numpy as np
+    center, csize, p2 = np.asarray(center), np.asarray(csize, dtype=np.float64), np.asarray(paras[:2])
+    ustart, vstart = center[:2] - (csize[:2] / 2.) / center[2] * p2 + 0.5
+    uend, vend = center[:2] + (csize[:2] / 2.) / center[2] * p2 + 0.5
+    return int(ustart), int(uend), int(vstart), int(vend), center[2] - csize[2] / 2., center[2] + csize[2] / 2.
+
+
+def center2transmat_np(center, csize, dsize, paras=NYU_PARAS):
+    """loader.py:210-240: crop affine (translate, isotropic scale, centring pad)."""
+    import numpy as np
+    ustart, uend, vstart, vend, _, _ = center2bounds_np(center, csize, paras)
+    trans1 = np.eye(3); trans1[0][2] = -ustart; trans1[1][2] = -vstart
+    w, h = (uend - ustart), (vend - vstart)
+    scale = min(dsize[0] / w, dsize[1] / h)
+    size = (int(w * scale), int(h * scale))
+    sc = scale * np.eye(3); sc[2][2] = 1
+    trans2 = np.eye(3)
+    trans2[0][2] = int(np.floor(dsize[0] / 2. - size[0] / 2.)); trans2[1][2] = int(np.floor(dsize[1] / 2. - size[1] / 2.))
+    return np.dot(trans2, np.dot(sc, trans1)).astype(np.float32)
+
+
+def crop_normalize_np(depth, center_uvd, center_z, cube, img_size, paras=NYU_PARAS):
+    """Loader.crop (loader.py:19-51) + Loader.normalize (:88-101) of one frame, cv2.resize(INTER_NEAREST) restated as its index
+    rule sx = min(floor(x * src_w / dst_w), src_w - 1) [verified against cv2 4.13 on random sizes].  depth (Hs, Ws) float32 mm (0 = invalid);
+    center_uvd (3,) float32; center_z the z of center_xyz used by normalize (nyu_loader.py:60).  Returns (img (D,D) float32, M (3,3) float32)."""
+    import numpy as np
+    dsize = np.array([img_size, img_size])
+    ustart, uend, vstart, vend, zstart, zend = center2bounds_np(center_uvd, cube, paras)
+    Hs, Ws = depth.shape
+    # bounds2crop (:190-207): slice + zero pad to the full box, then clamp depths to the cube
+    crop = np.zeros((vend - vstart, uend - ustart), np.float32)
+    v0, v1, u0, u1 = max(vstart, 0), min(vend, Hs), max(ustart, 0), min(uend, Ws)
+    if v1 > v0 and u1 > u0:
+        crop[v0 - vstart:v1 - vstart, u0 - ustart:u1 - ustart] = depth[v0:v1, u0:u1]
+    m1 = np.logical_and(crop < zstart, crop != 0); m2 = np.logical_and(crop > zend, crop != 0)
+    crop[m1] = zstart; crop[m2] = 0
+    w, h = (uend - ustart), (vend - vstart)
+    scale = min(dsize[0] / w, dsize[1] / h)
+    size = (int(w * scale), int(h * scale))
+    sx = np.minimum(np.floor(np.arange(size[0]) * (1.0 / (float(size[0]) / w))).astype(int), w - 1)
+    sy = np.minimum(np.floor(np.arange(size[1]) * (1.0 / (float(size[1]) / h))).astype(int), h - 1)
+    resized = crop[sy][:, sx]
+    res = np.zeros((img_size, img_size), np.float32)
+    us, vs = (dsize - size) / 2.
+    res[int(vs):int(vs + size[1]), int(us):int(us + size[0])] = resized
+    # normalize (:88-101)
+    cz = np.float64(center_z) if not isinstance(center_z, np.floating) else center_z
+    half = np.asarray(cube, dtype=np.float64)[2] / 2.
+    depth_max = res.max()
+    res[res == depth_max] = cz + half
+    res[res == 0] = cz + half
+    out = np.clip(res.astype(np.float64), cz - half, cz + half)
+    out = (out - cz) / half
+    return out.astype(np.float32), center2transmat_np(center_uvd, cube, dsize, paras)
+
+
+def preprocess_case_inputs(N: int, seed: int, Hs: int = 480, Ws: int = 640):
+    """Synthetic raw NYU-like frames: a hand-sized blob at 500-1000 mm over a far wall, invalid (0) speckles, a frame whose crop box
+    leaves the image on two sides, one with a very near object inside the box."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:Hs, 0:Ws]
+    frames, centers, cubes = [], [], []
+    for n in range(N):
+        z = rng.uniform(500, 1000)
+        cu, cv_ = (rng.uniform(60, Ws - 60), rng.uniform(60, Hs - 60)) if n % 3 else (rng.choice([15.0, Ws - 20.0]), rng.choice([12.0, Hs - 15.0]))
+        r = 588.0 * 90.0 / z
+        blob = ((xx - cu) ** 2 + (yy - cv_) ** 2) < r * r
+        d = np.full((Hs, Ws), rng.uniform(1500, 2500), np.float32) + rng.normal(0, 5, (Hs, Ws)).astype(np.float32)
+        d[blob] = (z + 40 * np.sin(xx / 9.0) + 30 * np.cos(yy / 7.0) + rng.normal(0, 2, (Hs, Ws)))[blob]
+        d[rng.rand(Hs, Ws) < 0.01] = 0
+        if n % 4 == 1:
+            d[int(cv_) - 5:int(cv_) + 5, int(cu) + 10:int(cu) + 25] = z - 400          # nearer than the cube front
+        d = np.round(d).astype(np.float32)                                             # 16-bit integer millimetres on the wire
+        frames.append(d)
+        centers.append(np.array([cu, cv_, z], np.float32))
+        cubes.append(np.array([300.0, 300.0, 300.0]) * (1.0 if n % 2 else 5.0 / 6.0))
+    return np.stack(frames), np.stack(centers), np.stack(cubes)
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8 d)
 # --------------------------------------------------------------------------------------
 def synthetic_batch(B: int, H: int, J: int, seed: int) -> Tuple[Tensor, Tensor]:

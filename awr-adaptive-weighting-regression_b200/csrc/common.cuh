@@ -3,9 +3,6 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
-#include <cstdlib>
-#include <mutex>
-#include <unordered_set>
 
 #define AWR_OK 0
 #define AWR_ERR_BAD_ARG (-1)
@@ -27,23 +24,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
 
 #ifdef __CUDACC__
-// AWR_SMEM_CARVEOUT=1: ask for the maximum shared-memory carve-out on EVERY kernel of the library, so that the L1/shared split of an SM
-// never has to be reconfigured between a tcgen05 convolution (≈ 205 KB of dynamic shared memory) and the streaming kernels around it --
-// kernels with different carve-outs cannot share an SM, which also keeps PDL from overlapping their prologues and tails.
-inline bool smem_carveout_enabled() {
-  static const bool on = [] { const char* e = getenv("AWR_SMEM_CARVEOUT"); return e ? (e[0] == '1') : false; }();
-  return on;
-}
-inline void maybe_set_carveout(const void* kernel) {
-  if (!smem_carveout_enabled()) return;
-  static std::mutex mu;
-  static std::unordered_set<const void*> done;            // per translation unit (inline statics are shared across them), keyed by kernel address
-  std::lock_guard<std::mutex> lock(mu);
-  if (done.insert(kernel).second) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  maybe_set_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];

@@ -383,7 +383,6 @@ cudaError_t launch_head_fwd(cudaStream_t st, const T* pred, const float* img, co
   at[1].id = cudaLaunchAttributeClusterDimension;
   at[1].val.clusterDim.x = S; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = (S > 1) ? 2 : 1;
-  maybe_set_carveout(reinterpret_cast<const void*>(head_fwd_kernel<T, S>));
   return cudaLaunchKernelEx(&cfg, head_fwd_kernel<T, S>, pred, img, uvd_gt, uvd_out, stats, partial, counter, loss_out, B, J, F, H, ks);
 }
 template <typename T>

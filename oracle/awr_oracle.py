@@ -1,8 +1,10 @@
 """CPU oracle for the AWR dense hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT.
 
-Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this file.  The product path (awr_b200) never does; it fails
-loudly when the CUDA library is missing.
+Only tests/ (+ tests/golden/make_*.py), __graft_entry__.smoke(), bench.py's cpu_baseline /
+--impl reference / parity / --gpu-eager-baseline legs and the developer scripts under tools/
+import this file, always as the checker, the timed CPU baseline or a seeded input generator.
+The product path (awr_b200) never does -- tests/test_abi.py greps the package for it -- and
+fails loudly when the CUDA library is missing.
 
 What this is: a plain restatement, in functional torch-CPU fp32 arithmetic, of
 the algorithm the reference runs on the path named by BASELINE.json:
@@ -18,10 +20,14 @@ batch_norm / max_pool2d / softmax) whose semantics are stable 1.1 -> 2.11; the
 restatement calls the same published primitives through torch.nn.functional on
 a flat state_dict, and writes the head / loss / coordinate grid in closed form.
 
-Parity pin: tests/golden/*.pt were produced by tests/golden/make_golden.py,
-which imports the UNMODIFIED reference modules from /root/reference in the
-build container and records their outputs on seeded inputs; tests/test_oracle.py
-checks every function here against those vectors.  (The reference ships no unit
+Also restated (numpy, same dtypes as the reference's code): util/eval_tool.py::EvalUtil and the
+non-augmented depth preprocessing of dataloader/loader.py.
+
+Parity pin: tests/golden/* were produced by tests/golden/make_golden.py, make_eval_golden.py and
+make_preprocess_golden.py, which import the UNMODIFIED reference modules from /root/reference
+(with the real cv2) in the build container and record their outputs on seeded inputs;
+tests/test_oracle.py, test_eval.py and test_preprocess.py check every function here against
+those vectors (the numpy restatements bit-exactly).  (The reference ships no unit
 tests or known-answer vectors of its own: SURVEY.md section 4.)
 """
 from __future__ import annotations

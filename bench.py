@@ -433,7 +433,10 @@ def main():
 
     parity = eager = None
     if rank == 0 and world == 1 and not a.no_parity and a.net == "resnet_18" and H == 128:
-        parity = parity_c1(dev)
+        try:
+            parity = parity_c1(dev)
+        except Exception as e:              # a checker leg must never cost the bench line
+            parity = {"error": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0 and world == 1 and a.gpu_eager_baseline:
         eager = {"unit": UNIT, "what": "oracle's torch ops on this GPU (eager, cuDNN), same train step, device-resident batch"}
         for key, ac in (("fp32", False), ("bf16_autocast", True)):

@@ -49,3 +49,35 @@ def max_over_ranks(value, device):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
     return float(value)
+
+
+def allreduce_busbw(flat, reps=10, group=None):
+    """Time `reps` sum all-reduces of `flat` alone (every rank must call this).  Returns (ms per all-reduce, max over ranks; bus bandwidth
+    in GB/s = 2 (n-1)/n * bytes / t, the figure NCCL quotes against the 900 GB/s per direction of NVLink 5; SURVEY.md section 8 d).
+    CUDA tensors are timed with CUDA events on the current stream, CPU tensors (gloo tests) with the wall clock.  The buffer is summed
+    `reps` times, so pass a scratch copy."""
+    import time
+    n = dist.get_world_size(group) if dist.is_initialized() else 1
+    if n <= 1:
+        return 0.0, 0.0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)          # warm-up (communicator / buffers)
+    if flat.is_cuda:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(group)
+        e0.record()
+        for _ in range(reps):
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+    else:
+        dist.barrier(group)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+    ms = max_over_ranks(ms, flat.device)
+    nbytes = flat.numel() * flat.element_size()
+    return ms, (2.0 * (n - 1) / n * nbytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0
+

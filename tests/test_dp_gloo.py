@@ -50,8 +50,9 @@ def _worker(rank, world, port, out):
     m, v = torch.zeros_like(w), torch.zeros_like(w)
     O.adam_step(w, g / world, m, v, 1)                       # grad_scale = 1/world, as awr_adam_flat applies it
     t = dp.max_over_ranks(rank + 1.0, "cpu")
+    ms, bw = dp.allreduce_busbw(torch.ones(1 << 16), reps=3)          # bench.py's all-reduce leg (wall clock under gloo)
     if rank == 0:
-        torch.save({"w": w, "g": g / world, "tmax": t}, out)
+        torch.save({"w": w, "g": g / world, "tmax": t, "ar_ms": ms, "ar_bw": bw}, out)
     torch.distributed.destroy_process_group()
 
 
@@ -71,3 +72,4 @@ def test_dp_world2_equals_single_process_on_concatenated_batch(tmp_path):
     O.adam_step(w, g, m, v, 1)
     assert torch.allclose(got["w"], w, rtol=1e-5, atol=1e-7)
     assert got["tmax"] == 2.0
+    assert got["ar_ms"] > 0 and got["ar_bw"] > 0

@@ -102,9 +102,23 @@ def parity_c1(dev):
         pred = m(img.to(dev))
         uvd = awr_b200.FeatureModule().offset2joint_softmax(pred, img.to(dev), c["ks"])
     diff = (uvd.cpu() - c["eval_uvd"][0]).abs().max().item()
+    mm = mean3d_diff_mm(uvd.cpu(), c["eval_uvd"][0], c["B"], c["J"], c["H"])
     return {"config": "resnet_18-deconv + AWR head, 1x128x128 depth crop, 14 joints, batch 1, fp32 forward (eval-mode BN)",
-            "uvd_max_abs_diff": diff, "tolerance": 1e-3, "pass": diff < 1e-3,
+            "uvd_max_abs_diff": diff, "tolerance": 1e-3, "pass": diff < 1e-3 and mm < 0.05,
+            "mean_3d_error_diff_mm": mm, "tolerance_mm": 0.05,
             "against": "unmodified reference on CPU, recorded in tests/golden/backbone_cases.pt[0] by tests/golden/make_golden.py"}
+
+
+def mean3d_diff_mm(uvd_ours, uvd_ref, B, J, img_size):
+    """north_star's second bound: |mean 3-D error(ours) - mean 3-D error(reference)| in mm on the same synthetic batch, through the
+    reference's UVD -> XYZ chain (util/eval_tool.py:34-49) with a synthetic NYU-like crop geometry and ground truth (checker role)."""
+    import torch
+    from oracle import awr_oracle as O
+    _, gt, center, M, cube, _ = O.eval_case_inputs(B, J, 77, img_size)
+    t = lambda a: torch.from_numpy(a)
+    e_ours = O.mean_3d_error_mm(uvd_ours.float(), t(gt), t(center), t(M), t(cube), img_size)
+    e_ref = O.mean_3d_error_mm(uvd_ref.float(), t(gt), t(center), t(M), t(cube), img_size)
+    return abs(e_ours - e_ref)
 
 
 def gpu_eager_steps(net, ds, ks, batch, dev, steps=10, autocast=False):

@@ -15,7 +15,9 @@ def test_reference_import_lines_resolve_to_awr_b200():
         "from model.resnet_deconv import get_deconv_net\n"
         "from model.loss import My_SmoothL1Loss\n"
         "from util.feature_tool import FeatureModule\n"
+        "from util.eval_tool import EvalUtil\n"                                  # train.py:18 / test.py:16
         "import awr_b200\n"
+        "assert EvalUtil is awr_b200.EvalUtil\n"
         "assert get_deconv_net is awr_b200.get_deconv_net and PoseNet is awr_b200.PoseNet\n"
         "assert My_SmoothL1Loss is awr_b200.My_SmoothL1Loss and FeatureModule is awr_b200.FeatureModule\n"
         "m = get_deconv_net(18, 14, 2); assert len(m.state_dict()) == 142\n"

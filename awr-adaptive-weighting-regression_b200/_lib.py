@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libawr_b200.so")
+LIB_PATH = os.environ.get("AWR_B200_LIB") or os.path.join(_HERE, "libawr_b200.so")      # override: debug builds (make PROFILE=1)
 
 F32, BF16 = 0, 1
 HUBER_MAX_BLOCKS = 1184
@@ -61,6 +61,26 @@ def lib():
 
 def exported_symbols():
     return list(_PROTOS)
+
+
+# ---- order-independent accumulators (awr_acc_t in include/awr_b200.h): value = hi * 2^-24 + lo * 2^-72 ---------------------
+def acc_zeros(n, device):
+    """n zero-initialised awr_acc_t (BatchNorm `sums` / `dsums` buffers of the C ABI)."""
+    return torch.zeros(n, 2, dtype=torch.int64, device=device)
+
+
+def acc_to_float(t):
+    """awr_acc_t[n] -> float64[n]."""
+    t = t.view(-1, 2)
+    return t[:, 0].double() * 2.0 ** -24 + t[:, 1].double() * 2.0 ** -72
+
+
+def acc_from_float(v):
+    """float[n] -> awr_acc_t[n] (for callers that computed the sums themselves)."""
+    v = v.double().flatten()
+    hi = torch.round(v * 2.0 ** 24)
+    lo = torch.round((v - hi * 2.0 ** -24) * 2.0 ** 72)
+    return torch.stack([hi.long(), lo.long()], dim=1).contiguous()
 
 
 def check(rc: int, what: str):

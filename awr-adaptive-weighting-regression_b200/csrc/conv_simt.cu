@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_pair_kernel(const float* __res
 // BatchNorm batch statistics (per-channel sum / sum of squares of the stored values) so no separate reduction pass is needed.
 template <typename T, int K>
 __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                              T* __restrict__ y, float* __restrict__ stats, int N, int H, int W, int Cout) {
+                                                              T* __restrict__ y, AwrAcc* __restrict__ stats, int N, int H, int W, int Cout) {
   pdl_entry();
   extern __shared__ __align__(16) float ws[];   // [K*K][Cout] then reduction scratch
   for (int i = threadIdx.x; i < K * K * Cout; i += blockDim.x) ws[i] = w[i];
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __res
     for (int q = 0; q < 8; ++q) { s1[q] = warp_sum(s1[q]); s2[q] = warp_sum(s2[q]); }
     if (lane == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { atomicAdd(stats + cg * 8 + q, s1[q]); atomicAdd(stats + Cout + cg * 8 + q, s2[q]); }
+      for (int q = 0; q < 8; ++q) { acc_add(stats + cg * 8 + q, s1[q]); acc_add(stats + Cout + cg * 8 + q, s2[q]); }
     }
   } else if (stats) {
     // threads with equal (threadIdx % G) share a channel octet: reduce over them in shared memory, one atomic per channel per block
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __res
       const int which = ch / Cout, c = ch % Cout, g = c >> 3, q = c & 7;
       float sum = 0.f;
       for (int r = g; r < (int)blockDim.x; r += G) sum += red[r * 16 + which * 8 + q];
-      atomicAdd(stats + which * Cout + c, sum);
+      acc_add(stats + which * Cout + c, sum);
     }
   }
 }
@@ -543,7 +543,7 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, 
   return AWR_OK;
 }
 
-int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, float* stats, int dtype, int N, int H, int W, int Cout, int k,
+int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, void* stats, int dtype, int N, int H, int W, int Cout, int k,
                   void* stream) {
   AWR_HOST_CHECK(x && w && y && N > 0 && Cout % 8 == 0 && k % 2 == 1 && k <= 7);
   if (k == 5 && W % 4 == 0 && (256 % (Cout / 8)) == 0 && (reinterpret_cast<unsigned long long>(x) & 15ull) == 0ull) {   // 16-byte patch loads
@@ -552,7 +552,7 @@ int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, fl
     if (blocks4 > 148 * 8) blocks4 = 148 * 8;
     size_t smem4 = (size_t)k * k * Cout * sizeof(float);
     if (smem4 < 256 * 16 * sizeof(float)) smem4 = 256 * 16 * sizeof(float);
-    DISPATCH_T(dtype, launch_pdl(stem_conv_tiled_kernel<T, 5>, dim3((int)blocks4), dim3(256), smem4, (cudaStream_t)stream, x, w, bias, (T*)y, stats, N, H, W, Cout));
+    DISPATCH_T(dtype, launch_pdl(stem_conv_tiled_kernel<T, 5>, dim3((int)blocks4), dim3(256), smem4, (cudaStream_t)stream, x, w, bias, (T*)y, (AwrAcc*)stats, N, H, W, Cout));
     AWR_LAUNCH_CHECK();
     return AWR_OK;
   }

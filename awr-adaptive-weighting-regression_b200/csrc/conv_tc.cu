@@ -56,7 +56,7 @@ __device__ unsigned long long g_conv_prof[148 * 8];
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ bias,
-               void* __restrict__ outp, float* __restrict__ stats, const __grid_constant__ ConvTcParams p) {
+               void* __restrict__ outp, AwrAcc* __restrict__ stats, const __grid_constant__ ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();                 // the next kernel may start its prologue while this grid runs
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2];
@@ -70,10 +70,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int b_bytes = p.Ntile * 128;
   const int stage_bytes = kABytes + b_bytes;
   const int total_tiles = p.nclasses * p.tiles_m * p.tiles_c;
-  // per-CTA BatchNorm partial sums [2*Cn] (fp32) behind the pipeline stages: flushed with one global atomic per channel at the end
+  // per-CTA BatchNorm partial sums behind the pipeline stages: one private [2*Cn] fp32 slice per epilogue warp (a single writer per
+  // element, so no shared-memory atomics and a fixed summation order), combined in warp order at the end and flushed through the
+  // order-independent global accumulators (AwrAcc) -- the statistics are bit-reproducible
   float* s_stats = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)p.stages * stage_bytes);
   if (stats) {
-    for (int i = threadIdx.x; i < 2 * p.Cn; i += kThreads) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 2 * p.Cn; i += kThreads) s_stats[i] = 0.f;
   }
 
   if (threadIdx.x == 0) {
@@ -138,7 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.Ntile);
       for (int it = 0; it < iters; ++it) {
         { PROF_T0(); mbar_wait(&full_bar[stage], phase); if (lane == 0) PROF_ADD(1); }
-        tc_fence_after();
+        tc_loop_fence();
         if (elect_one()) {
           const uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * sstep);
           const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)stage * sstep);
@@ -219,8 +221,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               s2[i] = k2 + __shfl_xor_sync(0xffffffffu, d2, st);
             }
           }
-          atomicAdd(s_stats + c0 + ch + lane, s1[0]);
-          atomicAdd(s_stats + p.Cn + c0 + ch + lane, s2[0]);
+          float* mine = s_stats + q * 2 * p.Cn;          // lane L owns channel c0+ch+L of this warp's slice
+          mine[c0 + ch + lane] += s1[0];
+          mine[p.Cn + c0 + ch + lane] += s2[0];
           if (!valid) continue;
         }
         if (p.out_mode == 0) {
@@ -265,8 +268,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (stats) {
     for (int i = threadIdx.x; i < 2 * p.Cn; i += kThreads) {
-      const float v = s_stats[i];
-      if (v != 0.f) atomicAdd(stats + i, v);
+      const float v = ((s_stats[i] + s_stats[2 * p.Cn + i]) + s_stats[4 * p.Cn + i]) + s_stats[6 * p.Cn + i];
+      if (v != 0.f) acc_add(stats + i, v);
     }
   }
   if (warp == 5) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
@@ -303,7 +306,7 @@ bool conv_make_weight_map(CUtensorMap* m, const ConvGeom& g, const void* w, int 
 
 extern "C" {
 
-int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, float* stats, int N, int Hi, int Wi, int Ck, int Ho, int Wo,
+int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, void* stats, int N, int Hi, int Wi, int Ck, int Ho, int Wo,
                 int Cn, int R, int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode, int n_valid,
                 int accumulate, void* stream) {
   AWR_HOST_CHECK(in && w && out && N > 0 && Ck % 64 == 0 && Cn % 64 == 0 && R > 0 && S > 0 && R * S <= kMaxTaps);
@@ -344,7 +347,8 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
         }
       }
   }
-  if (conv_halo_supported(g) && !getenv("AWR_B200_NO_HALO")) return conv_halo_launch(g, in, w, bias, out, stats, (cudaStream_t)stream);
+  static const bool no_halo = getenv("AWR_B200_NO_HALO") != nullptr;          // debugging switch, read once
+  if (conv_halo_supported(g) && !no_halo) return conv_halo_launch(g, in, w, bias, out, stats, (cudaStream_t)stream);
 
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
@@ -372,7 +376,7 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
   }
   p.tiles_c = Cn / p.Ntile;
   const int stage_bytes = kABytes + p.Ntile * 128;
-  const int stats_bytes = stats ? 2 * Cn * (int)sizeof(float) : 0;
+  const int stats_bytes = stats ? 4 * 2 * Cn * (int)sizeof(float) : 0;
   p.stages = (200 * 1024 - stats_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + stats_bytes;
@@ -395,7 +399,7 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
   const int total_tiles = p.nclasses * p.tiles_m * p.tiles_c;
   int sms = 148;
   int grid = total_tiles < sms ? total_tiles : sms;
-  if (launch_pdl(conv_tc_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, tmA, tmB, bias, out, stats, p) != cudaSuccess) return (int)cudaGetLastError();
+  if (launch_pdl(conv_tc_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, tmA, tmB, bias, out, reinterpret_cast<AwrAcc*>(stats), p) != cudaSuccess) return (int)cudaGetLastError();
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -25,4 +25,4 @@ struct ConvGeom {
 
 bool conv_make_weight_map(CUtensorMap* m, const ConvGeom& g, const void* w, int Ntile);
 bool conv_halo_supported(const ConvGeom& g);
-int conv_halo_launch(const ConvGeom& g, const void* in, const void* w, const float* bias, void* out, float* stats, cudaStream_t stream);
+int conv_halo_launch(const ConvGeom& g, const void* in, const void* w, const float* bias, void* out, void* stats /* AwrAcc[2*Cn] or NULL */, cudaStream_t stream);

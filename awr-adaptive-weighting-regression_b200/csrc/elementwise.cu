@@ -42,10 +42,10 @@ inline int ew_unroll() {
 }
 inline bool chan_ok(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
 
-// reduce NV per-thread 8-channel accumulators over the threads of a block that share a channel group, then
-// atomically add into out[v*C + c].  smem: kEwThreads * 8 floats.
+// reduce NV per-thread 8-channel accumulators over the threads of a block that share a channel group (fixed order), then add the
+// block's partial into the order-independent accumulators out[v*C + c] (AwrAcc, common.cuh).  smem: kEwThreads * 8 floats.
 template <int NV>
-__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int G, int C, float* __restrict__ out, float* smem) {
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int G, int C, AwrAcc* __restrict__ out, float* smem) {
   const int cg = threadIdx.x % G, rows = kEwThreads / G;
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int G,
       const int g = ch >> 3, k = ch & 7;
       float s = 0.f;
       for (int r = 0; r < rows; ++r) s += smem[(r * G + g) * 8 + k];
-      atomicAdd(out + v * C + ch, s);
+      acc_add(out + v * C + ch, s);
     }
   }
   (void)cg;
@@ -68,7 +68,8 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int G,
 // per-channel sum / sum of squares of an NHWC tensor:  sums[0:C] += sum_m x, sums[C:2C] += sum_m x^2
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kEwThreads) channel_stats_kernel(const T* __restrict__ x, long long M, int C, float* __restrict__ sums, int with_sq) {
+__global__ void __launch_bounds__(kEwThreads) channel_stats_kernel(const T* __restrict__ x, long long M, int C, AwrAcc* __restrict__ sums, int with_sq,
+                                                                   float* __restrict__ out_f32, unsigned* __restrict__ counter) {
   pdl_entry();
   __shared__ float smem[kEwThreads * 8];
   constexpr int U = 4;                        // four 16-byte loads in flight per thread (see Raw8)
@@ -95,12 +96,27 @@ __global__ void __launch_bounds__(kEwThreads) channel_stats_kernel(const T* __re
     for (int k = 0; k < 8; ++k) a1[0][k] = acc[0][k];
     block_channel_reduce<1>(a1, G, C, sums, smem);
   }
+  if (out_f32) {
+    // the CTA that arrives last adds the finished totals to the fp32 destination (bias gradients live in the flat fp32 gradient buffer):
+    // a single writer after an order-independent accumulation, so the result is bit-reproducible.  The ticket counter re-arms itself.
+    __shared__ unsigned last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      const int nv = with_sq ? 2 * C : C;
+      for (int c = threadIdx.x; c < nv; c += kEwThreads) out_f32[c] += acc_get_cg(sums + c);
+      if (threadIdx.x == 0) *counter = 0u;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // BN finalize: sums -> (scale, shift) for the apply pass, (mean, invstd) saved for backward, running stats
 // ---------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const AwrAcc* __restrict__ sums, float count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale_shift,
                                    float* __restrict__ mean_invstd, int C, float momentum, float eps, int training) {
@@ -108,8 +124,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float count, 
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
     float mean, invstd;
     if (training) {
-      mean = sums[c] / count;
-      float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+      mean = acc_get(sums + c) / count;
+      float var = fmaxf(acc_get(sums + C + c) / count - mean * mean, 0.f);
       invstd = rsqrtf(var + eps);
       if (running_mean) {
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
@@ -171,14 +187,14 @@ affine_act_kernel(const T* __restrict__ y, const float* __restrict__ ss, const T
 // block 0 also updates the running statistics / num_batches_tracked and saves (mean, invstd) for backward.
 // ---------------------------------------------------------------------------------------------------------
 struct BnSet {
-  const float* sums; const float* gamma; const float* beta; float* running_mean; float* running_var; long long* nbt; float* mean_invstd;
+  const AwrAcc* sums; const float* gamma; const float* beta; float* running_mean; float* running_var; long long* nbt; float* mean_invstd;
 };
 
 __device__ __forceinline__ void bn_coeffs(const BnSet& b, int c, int C, float inv_count, float eps, int training, float& sc, float& sh, float& mean,
                                           float& invstd, float& var) {
   if (training) {
-    mean = b.sums[c] * inv_count;
-    var = fmaxf(b.sums[C + c] * inv_count - mean * mean, 0.f);
+    mean = acc_get(b.sums + c) * inv_count;
+    var = fmaxf(acc_get(b.sums + C + c) * inv_count - mean * mean, 0.f);
   } else {
     mean = b.running_mean[c];
     var = b.running_var[c];
@@ -200,9 +216,19 @@ __device__ __forceinline__ void load8f(const float* __restrict__ p, float (&v)[8
 }
 // scale / shift of channels c0..c0+7.  All eight vector loads are issued before the first rsqrt: with scalar bn_coeffs() calls the
 // compiler serialises load -> rsqrt per channel, i.e. up to 16 dependent L2 round trips (3-6 us) at the head of every BatchNorm launch.
-__device__ __forceinline__ void bn_coeffs8(const BnSet& b, int c0, int C, float inv_count, float eps, int training, float (&sc)[8], float (&sh)[8]) {
+// Training: the batch sums come from `s_sums` = the CTA's shared-memory float copy of the 2C accumulators (acc_table(); converting the
+// 16-byte accumulators per thread costs 64 registers and sixteen scattered 16-byte loads per thread).
+constexpr int kMaxBnChannels = 2048;
+__device__ __forceinline__ void acc_table(const AwrAcc* __restrict__ src, int n, float* s_out) {      // CTA-cooperative; caller synchronises
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_out[i] = acc_value(*reinterpret_cast<const longlong2*>(src + i));
+}
+__device__ __forceinline__ void bn_coeffs8(const BnSet& b, const float* s_sums, int c0, int C, float inv_count, float eps, int training,
+                                           float (&sc)[8], float (&sh)[8]) {
   float m[8], v[8], g[8], be[8];
-  if (training) { load8f(b.sums + c0, m); load8f(b.sums + C + c0, v); }
+  if (training) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { m[k] = s_sums[c0 + k]; v[k] = s_sums[C + c0 + k]; }
+  }
   else { load8f(b.running_mean + c0, m); load8f(b.running_var + c0, v); }
   load8f(b.gamma + c0, g); load8f(b.beta + c0, be);
 #pragma unroll
@@ -263,8 +289,14 @@ bn_act_kernel(const T* __restrict__ y, BnSet bn, const T* __restrict__ res, BnSe
   if (i0 + step < items) load_batch(yb, rb, i0 + step);
   const float inv_count = 1.0f / count;
   float sc[8], sh[8], rsc[8], rsh[8];
-  bn_coeffs8(bn, c0, C, inv_count, eps, training, sc, sh);
-  if (res_has_bn) bn_coeffs8(rbn, c0, C, inv_count, eps, training, rsc, rsh);
+  __shared__ float s_sums[2][2 * kMaxBnChannels];
+  if (training) {
+    acc_table(bn.sums, 2 * C, s_sums[0]);
+    if (res_has_bn) acc_table(rbn.sums, 2 * C, s_sums[1]);
+    __syncthreads();
+  }
+  bn_coeffs8(bn, s_sums[0], c0, C, inv_count, eps, training, sc, sh);
+  if (res_has_bn) bn_coeffs8(rbn, s_sums[1], c0, C, inv_count, eps, training, rsc, rsh);
   auto process = [&](const Raw8<T> (&ry)[U], const Raw8<T> (&rr)[U], long long i0) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -317,7 +349,9 @@ bn_relu_maxpool_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ ou
   const long long items = (long long)N * Ho * Wo * G, stride = (long long)gridDim.x * kEwThreads;
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
   float sc[8], sh[8];
-  bn_coeffs8(bn, c0, C, 1.0f / count, eps, training, sc, sh);
+  __shared__ float s_sums[2 * kMaxBnChannels];
+  if (training) { acc_table(bn.sums, 2 * C, s_sums); __syncthreads(); }
+  bn_coeffs8(bn, s_sums, c0, C, 1.0f / count, eps, training, sc, sh);
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
     long long t = i / G;
     const int wo = (int)(t % Wo); t /= Wo;
@@ -365,7 +399,9 @@ bn_relu_maxpool3_fwd_kernel(const T* __restrict__ y, BnSet bn, T* __restrict__ o
   const int c0 = (int)(((long long)blockIdx.x * kEwThreads + threadIdx.x) % G) * 8;
   const float inv_count = 1.0f / count;
   float sc[8], sh[8];
-  bn_coeffs8(bn, c0, C, inv_count, eps, training, sc, sh);
+  __shared__ float s_sums[2 * kMaxBnChannels];
+  if (training) { acc_table(bn.sums, 2 * C, s_sums); __syncthreads(); }
+  bn_coeffs8(bn, s_sums, c0, C, inv_count, eps, training, sc, sh);
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
     long long t = i / G;
     const int wo = (int)(t % Wo); t /= Wo;
@@ -448,7 +484,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads)
 maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restrict__ idx, const T* __restrict__ y,
                       const float* __restrict__ mean_invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
+                      AwrAcc* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
                       int C, int Ho, int Wo, int k, int s, int p, int pass, int accumulate_param_grads) {
   pdl_entry();
   __shared__ float smem[kEwThreads * 8];
@@ -461,7 +497,7 @@ maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restri
   for (int q = 0; q < 8; ++q) {
     mean[q] = mean_invstd[c0 + q]; istd[q] = mean_invstd[C + c0 + q];
     sc[q] = gamma[c0 + q] * istd[q]; sh[q] = beta[c0 + q] - mean[q] * sc[q];
-    k1[q] = pass ? dsums[c0 + q] * invM : 0.f; k2[q] = pass ? dsums[C + c0 + q] * invM : 0.f;
+    k1[q] = pass ? acc_get(dsums + c0 + q) * invM : 0.f; k2[q] = pass ? acc_get(dsums + C + c0 + q) * invM : 0.f;
   }
   float acc[2][8] = {};
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < items; i += stride) {
@@ -501,8 +537,8 @@ maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restri
   if (pass == 0) block_channel_reduce<2>(acc, G, C, dsums, smem);
   else if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += kEwThreads) {
-      if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
-      else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
+      if (accumulate_param_grads) { dgamma[c] += acc_get(dsums + C + c); dbeta[c] += acc_get(dsums + c); }
+      else { dgamma[c] = acc_get(dsums + C + c); dbeta[c] = acc_get(dsums + c); }
     }
   }
 }
@@ -517,7 +553,7 @@ maxpool_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restri
 template <typename T, int U>
 __global__ void __launch_bounds__(kEwThreads, 2)
 pool_bn_bwd_reduce_kernel(const T* __restrict__ dpool, const T* __restrict__ pool_out, const float* __restrict__ gamma, const float* __restrict__ beta,
-                          long long M, int C, float* __restrict__ dsums) {
+                          long long M, int C, AwrAcc* __restrict__ dsums) {
   pdl_entry();
   __shared__ float smem[kEwThreads * 8];
   const int G = C >> 3;
@@ -563,7 +599,7 @@ template <typename T>
 __global__ void __launch_bounds__(kEwThreads, 2)
 maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __restrict__ idx, const T* __restrict__ y,
                          const float* __restrict__ mean_invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                         float* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
+                         AwrAcc* __restrict__ dsums, T* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int H, int W,
                          int C, int pass, int accumulate_param_grads) {
   pdl_entry();
   __shared__ float smem[kEwThreads * 8];
@@ -576,7 +612,7 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
   for (int q = 0; q < 8; ++q) {
     mean[q] = mean_invstd[c0 + q]; istd[q] = mean_invstd[C + c0 + q];
     sc[q] = gamma[c0 + q] * istd[q]; sh[q] = beta[c0 + q] - mean[q] * sc[q];
-    k1[q] = pass ? dsums[c0 + q] * invM : 0.f; k2[q] = pass ? dsums[C + c0 + q] * invM : 0.f;
+    k1[q] = pass ? acc_get(dsums + c0 + q) * invM : 0.f; k2[q] = pass ? acc_get(dsums + C + c0 + q) * invM : 0.f;
   }
   float acc[2][8] = {};
   for (long long it = (long long)blockIdx.x * kEwThreads + threadIdx.x; it < items; it += stride) {
@@ -651,8 +687,8 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
   if (pass == 0) block_channel_reduce<2>(acc, G, C, dsums, smem);
   else if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += kEwThreads) {
-      if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
-      else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
+      if (accumulate_param_grads) { dgamma[c] += acc_get(dsums + C + c); dbeta[c] += acc_get(dsums + c); }
+      else { dgamma[c] = acc_get(dsums + C + c); dbeta[c] = acc_get(dsums + c); }
     }
   }
 }
@@ -663,7 +699,7 @@ maxpool3s2_bn_bwd_kernel(const T* __restrict__ dpool, const unsigned char* __res
 template <typename T, int U>
 __global__ void __launch_bounds__(kEwThreads, 2)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
-                     const float* __restrict__ mean_invstd, long long M, int C, float* __restrict__ dsums,
+                     const float* __restrict__ mean_invstd, long long M, int C, AwrAcc* __restrict__ dsums,
                      const float* __restrict__ mask_gamma, const float* __restrict__ mask_beta) {
   pdl_entry();
   __shared__ float smem[kEwThreads * 8];
@@ -732,15 +768,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, 
 template <typename T, int U>
 __global__ void __launch_bounds__(kEwThreads, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y,
-                    const float* __restrict__ mean_invstd, const float* __restrict__ dsums, const float* __restrict__ gamma,
+                    const float* __restrict__ mean_invstd, const AwrAcc* __restrict__ dsums, const float* __restrict__ gamma,
                     T* dy, const T* dy_addend, T* dres, const T* dres_addend, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, long long M, int C, int accumulate_param_grads, const float* __restrict__ mask_beta) {
   pdl_entry();
   if (blockIdx.x == gridDim.x - 1) {       // dedicated CTA: dgamma / dbeta from the reduced sums, beside the streaming CTAs
     if (dgamma) {
       for (int c = threadIdx.x; c < C; c += kEwThreads) {
-        if (accumulate_param_grads) { dgamma[c] += dsums[C + c]; dbeta[c] += dsums[c]; }
-        else { dgamma[c] = dsums[C + c]; dbeta[c] = dsums[c]; }
+        if (accumulate_param_grads) { dgamma[c] += acc_get(dsums + C + c); dbeta[c] += acc_get(dsums + c); }
+        else { dgamma[c] = acc_get(dsums + C + c); dbeta[c] = acc_get(dsums + c); }
       }
     }
     return;
@@ -770,7 +806,12 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
   if (i0 + step < items) load_batch(bb, i0 + step);
   const float invM = 1.0f / (float)M;
   float mean[8], istd[8], k1[8], k2[8], gs[8], msh[8];
-  load8f(mean_invstd + c0, mean); load8f(mean_invstd + C + c0, istd); load8f(dsums + c0, k1); load8f(dsums + C + c0, k2); load8f(gamma + c0, gs);
+  load8f(mean_invstd + c0, mean); load8f(mean_invstd + C + c0, istd); load8f(gamma + c0, gs);
+  __shared__ float s_dsums[2 * kMaxBnChannels];
+  acc_table(dsums, 2 * C, s_dsums);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { k1[k] = s_dsums[c0 + k]; k2[k] = s_dsums[C + c0 + k]; }
   if (mask_beta) load8f(mask_beta + c0, msh);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -849,7 +890,7 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads, 1)
 bn_bwd_fused_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, const T* __restrict__ y, const float* __restrict__ mean_invstd,
-                    const float* __restrict__ gamma, const float* __restrict__ mask_beta, float* dsums, unsigned* barrier, T* dy,
+                    const float* __restrict__ gamma, const float* __restrict__ mask_beta, AwrAcc* dsums, unsigned* barrier, T* dy,
                     const T* dy_addend, T* dres, const T* dres_addend, float* __restrict__ dgamma, float* __restrict__ dbeta, long long items,
                     int C, float invM, int per, int accumulate_param_grads) {
   extern __shared__ __align__(128) unsigned char fsm[];
@@ -925,7 +966,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
   pdl_trigger();
   float k1[8], k2[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { k1[q] = __ldcg(dsums + c0 + q) * invM; k2[q] = __ldcg(dsums + C + c0 + q) * invM; }
+  for (int q = 0; q < 8; ++q) { k1[q] = acc_get_cg(dsums + c0 + q) * invM; k2[q] = acc_get_cg(dsums + C + c0 + q) * invM; }
   // pass 2: dy / dres from the shared-memory copy
   for (int k = threadIdx.x; k < n_local; k += kEwThreads) {
     const long long i = lo + k;
@@ -954,7 +995,7 @@ bn_bwd_fused_kernel(const T* __restrict__ dout, const T* __restrict__ act_out, c
   }
   if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += kEwThreads) {
-      const float sg = __ldcg(dsums + C + c), sb = __ldcg(dsums + c);
+      const float sg = acc_get_cg(dsums + C + c), sb = acc_get_cg(dsums + c);
       if (accumulate_param_grads) { dgamma[c] += sg; dbeta[c] += sb; }
       else { dgamma[c] = sg; dbeta[c] = sb; }
     }
@@ -1307,6 +1348,78 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void adam_tick_kernel(float* step_dev) {
   pdl_entry(); step_dev[0] += 1.f; }
 
+// Flat optimizer step with the hyper-parameters a schedule changes held in DEVICE memory (hyper = [step count (1-based, float), lr]), so
+// a CUDA graph that captured the launch follows StepLR / ReduceLROnPlateau without re-capture, and with a table of parameter spans
+// the step must not touch: torch.optim skips parameters whose .grad is None (the Hourglass skip_layer convs that forward never
+// calls, model/hourglass.py:38,45-48) -- with weight decay they would otherwise shrink.  Spans are 4-float aligned [begin, end).
+// SGD: buf = momentum*buf + (g + wd*p); p -= lr*buf (torch.optim.SGD, dampening 0, nesterov off; train.py:69) -- a zero-initialised
+// buffer reproduces torch's "first step copies the gradient".
+template <bool ADAM>
+__global__ void __launch_bounds__(kEwThreads)
+optim_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, bf16* __restrict__ shadow,
+             long long n, const float* __restrict__ hyper, float b1, float b2, float eps, float wd, float grad_scale,
+             const long long* __restrict__ skip, int n_skip, int zero_grad) {
+  pdl_entry();
+  __shared__ long long s_skip[2 * 256];
+  for (int i = threadIdx.x; i < 2 * n_skip; i += kEwThreads) s_skip[i] = skip[i];
+  if (n_skip) __syncthreads();
+  const float step = __ldg(hyper), lr = __ldg(hyper + 1);
+  float step_size = lr, inv_sqrt_bc2 = 1.f;
+  if (ADAM) {
+    const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+    step_size = lr / bc1; inv_sqrt_bc2 = rsqrtf(bc2);
+  }
+  const long long stride = (long long)gridDim.x * kEwThreads * 4;
+  for (long long i = ((long long)blockIdx.x * kEwThreads + threadIdx.x) * 4; i < n; i += stride) {
+    bool skipped = false;
+    for (int k = 0; k < n_skip; ++k) skipped |= (i >= s_skip[2 * k] && i < s_skip[2 * k + 1]);
+    if (skipped) continue;                  // never written by backward either, so there is nothing to re-zero
+    const int cnt = (i + 3 < n) ? 4 : (int)(n - i);
+    float pa[4], ga[4], ma[4], va[4];
+    if (cnt == 4) {
+      const float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i), mm = *reinterpret_cast<float4*>(m + i);
+      pa[0] = pp.x; pa[1] = pp.y; pa[2] = pp.z; pa[3] = pp.w; ga[0] = gg.x; ga[1] = gg.y; ga[2] = gg.z; ga[3] = gg.w;
+      ma[0] = mm.x; ma[1] = mm.y; ma[2] = mm.z; ma[3] = mm.w;
+      if (ADAM) { const float4 vv = *reinterpret_cast<float4*>(v + i); va[0] = vv.x; va[1] = vv.y; va[2] = vv.z; va[3] = vv.w; }
+    } else {
+      for (int k = 0; k < cnt; ++k) { pa[k] = p[i + k]; ga[k] = g[i + k]; ma[k] = m[i + k]; if (ADAM) va[k] = v[i + k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k >= cnt) break;
+      const float gr = ga[k] * grad_scale + wd * pa[k];
+      if (ADAM) {
+        ma[k] = b1 * ma[k] + (1.f - b1) * gr;
+        va[k] = b2 * va[k] + (1.f - b2) * gr * gr;
+        pa[k] -= step_size * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+      } else {
+        ma[k] = b1 * ma[k] + gr;               // b1 = momentum
+        pa[k] -= lr * ma[k];
+      }
+    }
+    if (zero_grad) {                        // the gradient buffer is consumed: leave it zeroed for the next step's accumulating wgrads
+      if (cnt == 4) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else for (int k = 0; k < cnt; ++k) g[i + k] = 0.f;
+    }
+    if (cnt == 4) {
+      *reinterpret_cast<float4*>(p + i) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+      *reinterpret_cast<float4*>(m + i) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+      if (ADAM) *reinterpret_cast<float4*>(v + i) = make_float4(va[0], va[1], va[2], va[3]);
+      if (shadow) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(pa[0], pa[1]), hi = __floats2bfloat162_rn(pa[2], pa[3]);
+        uint2 pk; pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
+        *reinterpret_cast<uint2*>(shadow + i) = pk;
+      }
+    } else {
+      for (int k = 0; k < cnt; ++k) {
+        p[i + k] = pa[k]; m[i + k] = ma[k];
+        if (ADAM) v[i + k] = va[k];
+        if (shadow) shadow[i + k] = __float2bfloat16_rn(pa[k]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kEwThreads) cast_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
   pdl_entry();
   const long long stride = (long long)gridDim.x * kEwThreads;
@@ -1337,26 +1450,27 @@ __global__ void __launch_bounds__(kEwThreads) cast_f32_to_bf16_kernel(const floa
 
 extern "C" {
 
-int awr_channel_stats(const void* x, int dtype, long long M, int C, float* sums, int with_sq, void* stream) {
-  AWR_HOST_CHECK(x && sums && M > 0 && chan_ok(C));
-  DISPATCH_T(dtype, launch_pdl(channel_stats_kernel<T>, dim3(ew_grid(M * (C / 8), 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)x, M, C, sums, with_sq));
+int awr_channel_stats(const void* x, int dtype, long long M, int C, void* sums, int with_sq, float* out_f32, unsigned* counter, void* stream) {
+  AWR_HOST_CHECK(x && sums && M > 0 && chan_ok(C) && ((out_f32 == nullptr) == (counter == nullptr)));
+  DISPATCH_T(dtype, launch_pdl(channel_stats_kernel<T>, dim3(ew_grid(M * (C / 8), 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)x, M, C,
+                               (AwrAcc*)sums, with_sq, out_f32, counter));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
 
-int awr_bn_finalize(const float* sums, long long count, const float* gamma, const float* beta, float* running_mean,
+int awr_bn_finalize(const void* sums, long long count, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_invstd, int C,
                     float momentum, float eps, int training, void* stream) {
   AWR_HOST_CHECK(gamma && beta && scale_shift && C > 0 && (training ? (sums != nullptr && count > 0) : (running_mean && running_var)));
-  launch_pdl(bn_finalize_kernel, dim3((C + 255) / 256), dim3(256), 0, (cudaStream_t)stream, sums, (float)count, gamma, beta, running_mean, running_var,
+  launch_pdl(bn_finalize_kernel, dim3((C + 255) / 256), dim3(256), 0, (cudaStream_t)stream, (const AwrAcc*)sums, (float)count, gamma, beta, running_mean, running_var,
                                                                        num_batches_tracked, scale_shift, mean_invstd, C, momentum,
                                                                        eps, training);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
 
-int awr_bn_act(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
-               long long* num_batches_tracked, float* mean_invstd, const void* res, const float* res_sums, const float* res_gamma,
+int awr_bn_act(const void* y, const void* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+               long long* num_batches_tracked, float* mean_invstd, const void* res, const void* res_sums, const float* res_gamma,
                const float* res_beta, float* res_running_mean, float* res_running_var, long long* res_num_batches_tracked,
                float* res_mean_invstd, void* out, int dtype, long long M, int C, float momentum, float eps, int training, int relu,
                void* stream) {
@@ -1364,21 +1478,21 @@ int awr_bn_act(const void* y, const float* sums, const float* gamma, const float
   AWR_HOST_CHECK(training ? (sums != nullptr) : (running_mean && running_var));
   const int res_has_bn = res_gamma != nullptr;
   AWR_HOST_CHECK(!res_has_bn || (res && res_beta && (training ? (res_sums != nullptr) : (res_running_mean && res_running_var))));
-  BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
-  BnSet b{res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
+  BnSet a{(const AwrAcc*)sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
+  BnSet b{(const AwrAcc*)res_sums, res_gamma, res_beta, res_running_mean, res_running_var, res_num_batches_tracked, res_mean_invstd};
   DISPATCH_TU(dtype, launch_pdl(bn_act_kernel<T, (U >= 4 ? 2 : 1)>, dim3(ew_grid(M * (C / 8), (U >= 4 ? 4 : 2)) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream, (const T*)y, a,
                                 (const T*)res, b, res_has_bn, (T*)out, M, C, (float)M, momentum, eps, training, relu));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
 
-int awr_bn_relu_maxpool_fwd(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+int awr_bn_relu_maxpool_fwd(const void* y, const void* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                             long long* num_batches_tracked, float* mean_invstd, void* out, unsigned char* idx, int dtype, int N, int H, int W,
                             int C, int k, int s, int p, float momentum, float eps, int training, void* stream) {
   AWR_HOST_CHECK(y && out && gamma && beta && N > 0 && chan_ok(C) && k >= 1 && k <= 3 && s >= 1);
   AWR_HOST_CHECK(training ? (sums != nullptr) : (running_mean && running_var));
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
-  BnSet a{sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
+  BnSet a{(const AwrAcc*)sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
   if (k == 3 && ew_unroll() > 1) {
     DISPATCH_T(dtype, launch_pdl(bn_relu_maxpool3_fwd_kernel<T>, dim3(ew_grid((long long)N * Ho * Wo * (C / 8), 1)), dim3(kEwThreads), 0, (cudaStream_t)stream,
                           (const T*)y, a, (T*)out, idx, N, H, W, C, Ho, Wo, s, p, (float)((long long)N * H * W), momentum, eps, training));
@@ -1392,29 +1506,29 @@ int awr_bn_relu_maxpool_fwd(const void* y, const float* sums, const float* gamma
 }
 
 int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* y, const float* mean_invstd, const float* gamma,
-                       const float* beta, float* dsums, void* dy, float* dgamma, float* dbeta, int dtype, int N, int H, int W, int C, int k,
+                       const float* beta, void* dsums, void* dy, float* dgamma, float* dbeta, int dtype, int N, int H, int W, int C, int k,
                        int s, int p, int pass, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dpool && idx && y && mean_invstd && gamma && beta && dsums && N > 0 && chan_ok(C) && (pass == 0 || dy != nullptr));
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
   if (k == 3 && s == 2 && p == 1 && H % 2 == 0 && W % 2 == 0) {
     DISPATCH_T(dtype, launch_pdl(maxpool3s2_bn_bwd_kernel<T>, dim3(red_blocks((long long)N * Ho * Wo * 2, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
-                          (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, dsums, (T*)dy, dgamma, dbeta, N, H, W, C, pass,
+                          (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, (AwrAcc*)dsums, (T*)dy, dgamma, dbeta, N, H, W, C, pass,
                           accumulate_param_grads));
     AWR_LAUNCH_CHECK();
     return AWR_OK;
   }
   DISPATCH_T(dtype, launch_pdl(maxpool_bn_bwd_kernel<T>, dim3(red_blocks((long long)N * H * W, C)), dim3(kEwThreads), 0, (cudaStream_t)stream, 
-                        (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, dsums, (T*)dy, dgamma, dbeta, N, H, W, C, Ho, Wo, k, s, p,
+                        (const T*)dpool, idx, (const T*)y, mean_invstd, gamma, beta, (AwrAcc*)dsums, (T*)dy, dgamma, dbeta, N, H, W, C, Ho, Wo, k, s, p,
                         pass, accumulate_param_grads));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
 
-int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float* gamma, const float* beta, float* dsums, int dtype, long long M,
+int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float* gamma, const float* beta, void* dsums, int dtype, long long M,
                            int C, void* stream) {
   AWR_HOST_CHECK(dpool && pool_out && gamma && beta && dsums && M > 0 && chan_ok(C));
   DISPATCH_TU(dtype, launch_pdl(pool_bn_bwd_reduce_kernel<T, (U >= 4 ? 2 : 1)>, dim3(ew_grid(M * (C / 8), (U >= 4 ? 4 : 2))), dim3(kEwThreads), 0, (cudaStream_t)stream,
-                                (const T*)dpool, (const T*)pool_out, gamma, beta, M, C, dsums));
+                                (const T*)dpool, (const T*)pool_out, gamma, beta, M, C, (AwrAcc*)dsums));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -1429,21 +1543,21 @@ int awr_affine_act(const void* y, const float* scale_shift, const void* res, con
 }
 
 int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* mask_gamma,
-                      const float* mask_beta, int dtype, long long M, int C, float* dsums, void* stream) {
+                      const float* mask_beta, int dtype, long long M, int C, void* dsums, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && M > 0 && chan_ok(C) && ((mask_gamma == nullptr) == (mask_beta == nullptr)));
   DISPATCH_TU(dtype, launch_pdl(bn_bwd_reduce_kernel<T, (U >= 4 ? 2 : 1)>, dim3(ew_grid(M * (C / 8), (U >= 4 ? 4 : 2))), dim3(kEwThreads), 0, (cudaStream_t)stream,
-                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, dsums, mask_gamma, mask_beta));
+                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, M, C, (AwrAcc*)dsums, mask_gamma, mask_beta));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
 
-int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* dsums,
+int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const void* dsums,
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && dsums && gamma && dy && M > 0 && chan_ok(C));
   // up to five tensors are read per item here: half the batch depth of the other passes keeps the kernel at 128 registers = 2 CTAs per SM
   DISPATCH_T(dtype, launch_pdl(bn_bwd_apply_kernel<T, 1>, dim3(ew_grid(M * (C / 8), 2) + 1), dim3(kEwThreads), 0, (cudaStream_t)stream,
-                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
+                        (const T*)dout, (const T*)act_out, (const T*)y, mean_invstd, (const AwrAcc*)dsums, gamma, (T*)dy, (const T*)dy_addend, (T*)dres,
                         (const T*)dres_addend, dgamma, dbeta, M, C, accumulate_param_grads, mask_beta));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1478,7 +1592,7 @@ int awr_bn_bwd_fused_ok(long long M, int C, int dtype, int with_act) {
 }
 
 int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* gamma, const float* mask_beta,
-                     float* dsums, unsigned* barrier, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
+                     void* dsums, unsigned* barrier, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream) {
   AWR_HOST_CHECK(dout && y && mean_invstd && gamma && dsums && barrier && dy && M > 0 && chan_ok(C));
   int grid, per; size_t smem;
@@ -1493,7 +1607,7 @@ int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const
     attr_set[ti] = true;
   }
   DISPATCH_T(dtype, launch_pdl(bn_bwd_fused_kernel<T>, dim3(grid), dim3(kEwThreads), smem, (cudaStream_t)stream, (const T*)dout, (const T*)act_out,
-                               (const T*)y, mean_invstd, gamma, mask_beta, dsums, barrier, (T*)dy, (const T*)dy_addend, (T*)dres,
+                               (const T*)y, mean_invstd, gamma, mask_beta, (AwrAcc*)dsums, barrier, (T*)dy, (const T*)dy_addend, (T*)dres,
                                (const T*)dres_addend, dgamma, dbeta, M * (long long)(C / 8), C, 1.0f / (float)M, per, accumulate_param_grads));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
@@ -1583,6 +1697,31 @@ int awr_adam_flat(float* p, const float* g, float* m, float* v, void* bf16_shado
                                                                                 beta2, eps, weight_decay, grad_scale);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
+}
+
+int awr_optim_adam(float* p, float* g, float* m, float* v, void* bf16_shadow, long long n, const float* hyper_dev, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, const long long* skip_spans_dev, int n_skip, int zero_grad,
+                   void* stream) {
+  AWR_HOST_CHECK(p && g && m && v && hyper_dev && n > 0 && n_skip >= 0 && n_skip <= 256 && (n_skip == 0 || skip_spans_dev));
+  launch_pdl(optim_kernel<true>, dim3(ew_blocks((n + 3) / 4, 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, p, g, m, v, (bf16*)bf16_shadow, n, hyper_dev,
+             beta1, beta2, eps, weight_decay, grad_scale, skip_spans_dev, n_skip, zero_grad);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_optim_sgd(float* p, float* g, float* momentum_buf, void* bf16_shadow, long long n, const float* hyper_dev, float momentum,
+                  float weight_decay, float grad_scale, const long long* skip_spans_dev, int n_skip, int zero_grad, void* stream) {
+  AWR_HOST_CHECK(p && g && momentum_buf && hyper_dev && n > 0 && n_skip >= 0 && n_skip <= 256 && (n_skip == 0 || skip_spans_dev));
+  launch_pdl(optim_kernel<false>, dim3(ew_blocks((n + 3) / 4, 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, p, g, momentum_buf, (float*)nullptr,
+             (bf16*)bf16_shadow, n, hyper_dev, momentum, 0.f, 0.f, weight_decay, grad_scale, skip_spans_dev, n_skip, zero_grad);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_memset_zero(void* p, long long nbytes, void* stream) {
+  AWR_HOST_CHECK(p && nbytes > 0);
+  const cudaError_t e = cudaMemsetAsync(p, 0, (size_t)nbytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? AWR_OK : (int)e;
 }
 
 int awr_adam_tick(float* step_dev, void* stream) {

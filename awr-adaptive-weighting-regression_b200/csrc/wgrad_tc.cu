@@ -124,7 +124,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
     int stage = 0; uint32_t phase = 0;
     for (int it = 0; it < iters; ++it) {
       mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
+      tc_loop_fence();
       if (elect_one()) {
         const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
         const uint64_t bd = umma_desc_sw128(sa + b_off, 8192, 1024);

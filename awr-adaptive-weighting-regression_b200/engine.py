@@ -40,7 +40,7 @@ class ParamLayout:
     """Physical order of every weight is what the kernels read:
          conv   (Co,Ci,kh,kw) canonical  -> physical [kh][kw][Co][Ci]      (canonical = phys.permute(2,3,0,1))
          deconv (Ci,Co,kh,kw) canonical  -> physical [kh][kw][Co][Ci]      (canonical = phys.permute(3,2,0,1))
-         head   two 1x1 convs (3J / J rows) share one zero-padded [64][Cin] block; biases share one [64] block
+         head   two 1x1 convs (3J / J rows) share one zero-padded [align64(4J)][Cin] block; biases share one [align64(4J)] block
          vec    (C,)"""
 
     def __init__(self):
@@ -71,17 +71,19 @@ class ParamLayout:
         self.order.append(name)
 
     def head(self, gname, names_rows, cin, bias_names):
-        """names_rows: [(param name, rows)] stacked into one [64][cin] block (rows beyond the sum stay zero)."""
-        off = self._alloc(64 * cin)
-        self.groups[gname + ".weight"] = (off, (64, cin))
+        """names_rows: [(param name, rows)] stacked into one [align64(sum rows)][cin] block (rows beyond the sum stay zero):
+        64 rows for the 14/16-joint datasets, 128 for the 21-joint ones (config.py:1-6)."""
+        hc = _align(sum(r for _, r in names_rows))
+        off = self._alloc(hc * cin)
+        self.groups[gname + ".weight"] = (off, (hc, cin))
         r = 0
         for n, rows in names_rows:
             s = ParamSpec(n, "headw", (rows, cin, 1, 1), off + r * cin, (rows, cin))
             self.specs[n] = s
             self.order.append(n)
             r += rows
-        boff = self._alloc(64)
-        self.groups[gname + ".bias"] = (boff, (64,))
+        boff = self._alloc(hc)
+        self.groups[gname + ".bias"] = (boff, (hc,))
         r = 0
         for (n, rows) in zip(bias_names, [x[1] for x in names_rows]):
             s = ParamSpec(n, "vec", (rows,), boff + r, (rows,))
@@ -176,8 +178,8 @@ def hourglass_layout(nstack, J):
         lay.head(f"outs.{i}", [(f"outs_1.{i}.weight", 3 * J), (f"outs_2.{i}.weight", J)], 256, [f"outs_1.{i}.bias", f"outs_2.{i}.bias"])
     for i in range(nstack - 1):
         conv(f"merge_features.{i}.conv.conv", 256, 256, 1)
-        # merge_preds consumes the 4J-channel prediction volume, held as a 64-channel zero-padded NHWC activation
-        lay.conv(f"merge_preds.{i}.conv.conv.weight", 256, 4 * J, 1, ci_pad=64)
+        # merge_preds consumes the 4J-channel prediction volume, held as a zero-padded NHWC activation of align64(4J) channels
+        lay.conv(f"merge_preds.{i}.conv.conv.weight", 256, 4 * J, 1, ci_pad=_align(4 * J))
         lay.vec(f"merge_preds.{i}.conv.conv.bias", 256)
     return lay
 
@@ -193,7 +195,7 @@ class Act:
         self.t = torch.empty(N, H, W, C, dtype=dtype or plan.tdtype, device=plan.device)
         self.g = None
         self.gw = False          # gradient already written in the backward plan (next contribution accumulates)
-        self.stats = None        # fp32 [2C] per-channel sum / sum-of-squares filled by the producing conv's epilogue (bf16 mode)
+        self.stats = None        # awr_acc_t[2C] per-channel sum / sum-of-squares filled by the producing conv's epilogue (bf16 mode)
 
     @property
     def M(self):
@@ -205,12 +207,15 @@ class Act:
         return self.g
 
 
+ACC = 4          # floats per order-independent accumulator (awr_acc_t = 2 x int64, include/awr_b200.h)
+
+
 class BNState:
     def __init__(self, plan, prefix, C, sums=None):
         self.prefix, self.C = prefix, C
         self.fused_stats = sums is not None
-        self.sums = sums if sums is not None else plan.arena(2 * C)
-        self.dsums = plan.arena(2 * C)
+        self.sums = sums if sums is not None else plan.arena(ACC * 2 * C)
+        self.dsums = plan.arena(ACC * 2 * C)
         self.ss = torch.empty(2 * C, dtype=torch.float32, device=plan.device)
         self.mi = torch.empty(2 * C, dtype=torch.float32, device=plan.device)
 
@@ -509,7 +514,7 @@ class _Stem(_Op):
         w = plan.P(wname)        # physical [k][k][Cout][1] == [k*k][Cout]
         b = plan.P(bname) if bname else None
         if plan.training and k == 5:
-            self.y.stats = plan.arena(2 * Cout)          # BatchNorm statistics come out of the conv kernel itself
+            self.y.stats = plan.arena(ACC * 2 * Cout)    # BatchNorm statistics come out of the conv kernel itself
         plan.call(plan.fwd, "awr_stem_conv", plan.img, w, b, self.y.t, self.y.stats, plan.dt, B, H, H, Cout, k)
 
     def plan_bwd(self):
@@ -537,7 +542,7 @@ class _Conv(_Op):
         self.flops = 2 * coarse * self.Cin * Cout * k * k
         self.detail = f"{'deconv' if transposed else 'conv'}{k}x{k}s{stride} {self.Cin}->{Cout} @{x.H}->{Ho} N{x.N}"
         if plan.tc and plan.training and want_stats:
-            self.y.stats = plan.arena(2 * Cout)
+            self.y.stats = plan.arena(ACC * 2 * Cout)
         self._emit_fwd()
 
     def _emit_fwd(self):
@@ -564,7 +569,7 @@ class _Conv(_Op):
                 pl.call(pl.bwd, "awr_conv_wgrad_tc", x.t, dy, gW, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k, self.stride,
                         self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
             if self.bname:
-                pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
+                pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.arena(ACC * self.Cout), 0, pl.G(self.bname), pl.arena(1))
             w16 = pl.W16(self.wname)
 
             def emit_tc(dst, acc):
@@ -580,7 +585,7 @@ class _Conv(_Op):
             pl.call(pl.bwd, "awr_conv_wgrad_simt", x.t, dy, gW, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
                     self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
         if self.bname:
-            pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.G(self.bname), 0)
+            pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.arena(ACC * self.Cout), 0, pl.G(self.bname), pl.arena(1))
         # data gradient
         if True:
             w = pl.P(self.wname)
@@ -604,7 +609,7 @@ class _BNAct(_Op):
         tr = pl.training
         for t, bn in ((y, self.bn), (res_y, self.bn_res)):
             if bn is not None and tr and not bn.fused_stats:
-                pl.call(pl.fwd, "awr_channel_stats", t.t, pl.dt, t.M, t.C, bn.sums, 1)
+                pl.call(pl.fwd, "awr_channel_stats", t.t, pl.dt, t.M, t.C, bn.sums, 1, None, None)
 
         def bnset(bn):
             if bn is None:
@@ -670,7 +675,7 @@ class _BNPool(_Op):
         self.out = Act(plan, y.N, Ho, Wo, y.C)
         self.idx = torch.empty(y.N, Ho, Wo, y.C, dtype=torch.uint8, device=plan.device) if tr else None
         if tr and not self.bn.fused_stats:
-            pl.call(pl.fwd, "awr_channel_stats", y.t, pl.dt, y.M, y.C, self.bn.sums, 1)
+            pl.call(pl.fwd, "awr_channel_stats", y.t, pl.dt, y.M, y.C, self.bn.sums, 1, None, None)
         pl.call(pl.fwd, "awr_bn_relu_maxpool_fwd", y.t, self.bn.sums if tr else None, pl.P(prefix + ".weight"), pl.P(prefix + ".bias"),
                 pl.buf(prefix + ".running_mean"), pl.buf(prefix + ".running_var"), pl.buf(prefix + ".num_batches_tracked") if tr else None,
                 self.bn.mi, self.out.t, self.idx, pl.dt, y.N, y.H, y.W, y.C, k, s, p, BN_MOMENTUM, BN_EPS, int(tr))
@@ -759,64 +764,65 @@ class _UpAdd(_Op):
 
 class _Head(_Op):
     """final1 || final2 (resnet_deconv.py:52-53,133-136) / outs_1 || outs_2 (hourglass.py:135-136,153-157):
-    one 1x1 GEMM with N = 4J (padded to 64) writing the (B,4J,F,F) fp32 NCHW volume the AWR head consumes."""
+    one 1x1 GEMM with N = 4J (padded to a multiple of 64) writing the (B,4J,F,F) fp32 NCHW volume the AWR head consumes."""
 
     def __init__(self, plan, x, gname):
         self.plan, self.x, self.gname = plan, x, gname
         J = plan.J
+        HC = self.HC = _align(4 * J)
         self.pred = torch.empty(x.N, 4 * J, x.H, x.W, dtype=torch.float32, device=plan.device)
         self.dpred = torch.zeros_like(self.pred) if plan.training else None   # written by the head/loss backward (or autograd)
         self._nhwc = None
         pl = plan
         if pl.tc:
             pl.call(pl.fwd, "awr_conv_tc", x.t, pl.W16(gname + ".weight"), pl.P(gname + ".bias"), self.pred, None, x.N, x.H, x.W, x.C,
-                    x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
+                    x.H, x.W, HC, 1, 1, 1, 0, 0, 1, x.C, HC * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
         else:
             pl.call(pl.fwd, "awr_conv_simt", x.t, pl.P(gname + ".weight"), pl.P(gname + ".bias"), self.pred, pl.dt, x.N, x.H, x.W, x.C,
-                    x.H, x.W, 64, 1, 1, 1, 0, 0, 1, x.C, 64 * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
+                    x.H, x.W, HC, 1, 1, 1, 0, 0, 1, x.C, HC * x.C, 1, 4 * J, 0, flops=2 * x.M * x.C * 4 * J, tag="conv_fprop")
 
     def pred_nhwc(self):
-        """Prediction volume as a 64-channel NHWC activation (input of merge_preds in stacked hourglasses)."""
+        """Prediction volume as a zero-padded NHWC activation of align64(4J) channels (input of merge_preds in stacked hourglasses)."""
         if self._nhwc is None:
             pl, x = self.plan, self.x
-            self._nhwc = Act(pl, x.N, x.H, x.W, 64)
-            pl.call(pl.fwd, "awr_nchw_to_nhwc", self.pred, self._nhwc.t, pl.dt, x.N, 4 * pl.J, 64, x.H * x.W)
+            self._nhwc = Act(pl, x.N, x.H, x.W, self.HC)
+            pl.call(pl.fwd, "awr_nchw_to_nhwc", self.pred, self._nhwc.t, pl.dt, x.N, 4 * pl.J, self.HC, x.H * x.W)
         return self._nhwc
 
     def plan_bwd(self):
         pl, x = self.plan, self.x
-        J = pl.J
+        J, HC = pl.J, self.HC
         P = x.H * x.W
         has_direct = self.dpred is not None
         has_nhwc = self._nhwc is not None and self._nhwc.gw
         if not (has_direct or has_nhwc):
             return
         if self._nhwc is None:
-            self._nhwc = Act(pl, x.N, x.H, x.W, 64)
+            self._nhwc = Act(pl, x.N, x.H, x.W, HC)
         d = self._nhwc.grad()
         if has_direct:
             if has_nhwc:
                 tmp = torch.empty_like(d)
-                pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, tmp, pl.dt, x.N, 4 * J, 64, P)
+                pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, tmp, pl.dt, x.N, 4 * J, HC, P)
                 pl.call(pl.bwd, "awr_relu_bwd", tmp, None, d, d, pl.dt, d.numel())
             else:
-                pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, d, pl.dt, x.N, 4 * J, 64, P)
+                pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, d, pl.dt, x.N, 4 * J, HC, P)
         g = self.gname
         if pl.tc:
-            pl.call(pl.bwd, "awr_conv_wgrad_tc", d, x.t, pl.G(g + ".weight"), x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1, 64 * x.C,
+            pl.call(pl.bwd, "awr_conv_wgrad_tc", d, x.t, pl.G(g + ".weight"), x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1, HC * x.C,
                     flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
-            pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, 64, pl.G(g + ".bias"), 0)
+            pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, HC, pl.arena(ACC * HC), 0, pl.G(g + ".bias"), pl.arena(1))
 
             def emit_tc(dst, acc):
-                pl.call(pl.bwd, "awr_conv_tc", d, pl.W16(g + ".weight"), None, dst, None, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, 0,
-                        x.C, 1, 64 * x.C, 0, 0, int(acc), flops=2 * x.M * x.C * 4 * J, tag="conv_dgrad")
+                pl.call(pl.bwd, "awr_conv_tc", d, pl.W16(g + ".weight"), None, dst, None, x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, 0,
+                        x.C, 1, HC * x.C, 0, 0, int(acc), flops=2 * x.M * x.C * 4 * J, tag="conv_dgrad")
             _contribute(pl, x, emit_tc)
             return
-        pl.call(pl.bwd, "awr_conv_wgrad_simt", d, x.t, pl.G(g + ".weight"), pl.dt, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1,
-                64 * x.C, flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
-        pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, 64, pl.G(g + ".bias"), 0)
+        pl.call(pl.bwd, "awr_conv_wgrad_simt", d, x.t, pl.G(g + ".weight"), pl.dt, x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1,
+                HC * x.C, flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
+        pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, HC, pl.arena(ACC * HC), 0, pl.G(g + ".bias"), pl.arena(1))
 
         def emit(dst, acc):
-            pl.call(pl.bwd, "awr_conv_simt", d, pl.P(g + ".weight"), None, dst, pl.dt, x.N, x.H, x.W, 64, x.H, x.W, x.C, 1, 1, 1, 0, 0,
-                    x.C, 1, 64 * x.C, 0, 0, int(acc), flops=2 * x.M * x.C * 4 * J, tag="conv_dgrad")
+            pl.call(pl.bwd, "awr_conv_simt", d, pl.P(g + ".weight"), None, dst, pl.dt, x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, 0,
+                    x.C, 1, HC * x.C, 0, 0, int(acc), flops=2 * x.M * x.C * 4 * J, tag="conv_dgrad")
         _contribute(pl, x, emit)

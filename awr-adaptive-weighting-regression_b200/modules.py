@@ -163,10 +163,12 @@ class _BackboneFn(torch.autograd.Function):
             else:
                 h.dpred.copy_(g)
         pl.run_backward()
-        grads = []
-        for name, p in zip(module._pnames, module.parameters()):
-            gv = st.grad_view(name)
-            grads.append(gv.clone() if p.grad is not None else gv)      # never alias an existing .grad (AccumulateGrad adds in place)
+        # Always hand autograd private copies: AccumulateGrad may install (steal) the returned tensor as p.grad, and a view of the shared
+        # flat buffer would then be wiped by the next backward's zero fill / rewritten by its kernels (doubling every gradient under
+        # zero_grad(set_to_none=False) and losing the first micro-batch under gradient accumulation).  One flat copy, then views of it.
+        flat = st.grads.clone()
+        lay = st.layout
+        grads = [lay.view(flat, name).contiguous() for name in module._pnames]
         return (None, None) + tuple(grads)
 
 

@@ -85,12 +85,20 @@ int awr_crop_normalize(const void* src, int src_format, int N, int Hs, int Ws, c
  * per-channel reductions).  These replace nn.BatchNorm2d / nn.ReLU / residual adds / nn.MaxPool2d / nn.Upsample
  * of model/resnet_deconv.py:31-36,145-215 and model/hourglass.py:28-88. */
 
-/* sums[0:C] += sum_m x[m,c];  with_sq: sums[C:2C] += sum_m x[m,c]^2   (sums fp32, caller zero-fills) */
-int awr_channel_stats(const void* x, int dtype, long long M, int C, float* sums, int with_sq, void* stream);
+/* Per-channel accumulators shared by many CTAs (BatchNorm batch statistics `sums`, their backward sums `dsums`) are
+ * ORDER-INDEPENDENT: awr_acc_t[n], value = hi * 2^-24 + lo * 2^-72, filled with 64-bit integer atomics (every fp32 partial, |p| < 2^39,
+ * is split exactly), so the totals -- and with them the whole step's BatchNorm path -- are bit-reproducible run to run, which fp32
+ * atomics are not (the reference is bit-deterministic on CPU).  16 bytes per value, zero-filled by the caller. */
+typedef struct { long long hi, lo; } awr_acc_t;
+
+/* sums[0:C] += sum_m x[m,c];  with_sq: sums[C:2C] += sum_m x[m,c]^2   (sums: awr_acc_t[C or 2C], caller zero-fills).
+ * out_f32 + counter (both or neither; counter: one zero-initialised unsigned): the CTA finishing last ADDS the totals to the fp32
+ * array out_f32 (conv bias gradients inside the flat gradient buffer; single writer => reproducible) and re-arms the counter. */
+int awr_channel_stats(const void* x, int dtype, long long M, int C, void* sums, int with_sq, float* out_f32, unsigned* counter, void* stream);
 
 /* BatchNorm2d statistics -> per-channel affine.  training: batch stats from sums/count, running stats updated with
  * `momentum` (unbiased var), *num_batches_tracked += 1;  eval: running stats.  scale_shift[2C]; mean_invstd[2C] or NULL. */
-int awr_bn_finalize(const float* sums, long long count, const float* gamma, const float* beta, float* running_mean,
+int awr_bn_finalize(const void* sums, long long count, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, long long* num_batches_tracked, float* scale_shift, float* mean_invstd, int C,
                     float momentum, float eps, int training, void* stream);
 
@@ -98,27 +106,27 @@ int awr_bn_finalize(const float* sums, long long count, const float* gamma, cons
  * squares} over the M pixels (produced by awr_channel_stats or by awr_conv_tc's epilogue), running statistics updated (momentum,
  * unbiased variance), *num_batches_tracked += 1; eval: running statistics.  mean_invstd[2C] (or NULL) is saved for backward.
  * The res_* set (all NULL when absent) is the BatchNorm of the residual branch (ResNet downsample path, resnet_deconv.py:62-68). */
-int awr_bn_act(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
-               long long* num_batches_tracked, float* mean_invstd, const void* res, const float* res_sums, const float* res_gamma,
+int awr_bn_act(const void* y, const void* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+               long long* num_batches_tracked, float* mean_invstd, const void* res, const void* res_sums, const float* res_gamma,
                const float* res_beta, float* res_running_mean, float* res_running_var, long long* res_num_batches_tracked,
                float* res_mean_invstd, void* out, int dtype, long long M, int C, float momentum, float eps, int training, int relu,
                void* stream);
 
 /* Fused stem tail (resnet_deconv.py:33-35): out = MaxPool_{k,s,p}(ReLU(BN(y))) read from the raw conv output in ONE pass; idx = arg-max
  * tap byte per pooled element.  BN arguments as in awr_bn_act.  The full-resolution normalised tensor is never written. */
-int awr_bn_relu_maxpool_fwd(const void* y, const float* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+int awr_bn_relu_maxpool_fwd(const void* y, const void* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                             long long* num_batches_tracked, float* mean_invstd, void* out, unsigned char* idx, int dtype, int N, int H, int W,
                             int C, int k, int s, int p, float momentum, float eps, int training, void* stream);
 /* Backward of the above straight to dy (gradient of the raw conv output): pass 0 accumulates dsums[2C] = {sum dz, sum dz*yhat} (caller
  * zero-fills), pass 1 writes dy and dgamma/dbeta.  dz is rebuilt from dpool + idx (gather over <= 4 windows) and the ReLU mask from y. */
 int awr_maxpool_bn_bwd(const void* dpool, const unsigned char* idx, const void* y, const float* mean_invstd, const float* gamma,
-                       const float* beta, float* dsums, void* dy, float* dgamma, float* dbeta, int dtype, int N, int H, int W, int C, int k,
+                       const float* beta, void* dsums, void* dy, float* dgamma, float* dbeta, int dtype, int N, int H, int W, int C, int k,
                        int s, int p, int pass, int accumulate_param_grads, void* stream);
 
 /* Pass 0 of awr_maxpool_bn_bwd at pooled resolution (any k/s/p): dsums[0:C] += sum dpool*[pool_out>0], dsums[C:2C] += sum dpool*[pool_out>0]*
  * (pool_out-beta)/gamma, which equal sum dz and sum dz*yhat of the full-resolution pass because the pooled value is the activation at the
  * arg-max pixel.  dpool / pool_out: (M = N*Ho*Wo, C) NHWC. */
-int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float* gamma, const float* beta, float* dsums, int dtype, long long M,
+int awr_pool_bn_bwd_reduce(const void* dpool, const void* pool_out, const float* gamma, const float* beta, void* dsums, int dtype, long long M,
                            int C, void* stream);
 
 /* out = act( ss(y) + res_ss(res) ),  ss(v)[c] = v*scale[c] + shift[c]; scale_shift / res / res_scale_shift may be NULL. */
@@ -129,11 +137,11 @@ int awr_affine_act(const void* y, const float* scale_shift, const void* res, con
  * ReLU(BN(y)) WITHOUT residual, recomputed from y alone when mask_gamma/mask_beta (the BN affine) are given -- one tensor read less;
  * all three NULL: no ReLU. */
 int awr_bn_bwd_reduce(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* mask_gamma,
-                      const float* mask_beta, int dtype, long long M, int C, float* dsums, void* stream);
+                      const float* mask_beta, int dtype, long long M, int C, void* dsums, void* stream);
 /* BN backward pass 2 (mask_beta non-NULL: ReLU mask recomputed from y with gamma/mask_beta instead of reading act_out):
  * dy = bn_grad [+ dy_addend]; optional dres = dz [+ dres_addend] (addends may alias their outputs);
  * dgamma/dbeta (NULL to skip) written or accumulated. */
-int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* dsums,
+int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const void* dsums,
                      const float* gamma, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, const float* mask_beta, int dtype, long long M, int C, int accumulate_param_grads, void* stream);
 
@@ -146,7 +154,7 @@ int awr_bn_bwd_apply(const void* dout, const void* act_out, const void* y, const
  * The launch needs all its CTAs co-resident (grid <= SM count, one CTA per SM). */
 int awr_bn_bwd_fused_ok(long long M, int C, int dtype, int with_act);
 int awr_bn_bwd_fused(const void* dout, const void* act_out, const void* y, const float* mean_invstd, const float* gamma, const float* mask_beta,
-                     float* dsums, unsigned* barrier, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
+                     void* dsums, unsigned* barrier, void* dy, const void* dy_addend, void* dres, const void* dres_addend, float* dgamma,
                      float* dbeta, int dtype, long long M, int C, int accumulate_param_grads, void* stream);
 
 /* dx = dout*(act_out>0) [+ addend]   (act_out / addend may be NULL); n elements, n % 8 == 0 */
@@ -171,6 +179,20 @@ int awr_nhwc_to_nchw(const void* src, float* dst, int dtype, int N, int Csrc, in
 int awr_adam_flat(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, const float* step_dev, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 int awr_adam_tick(float* step_dev, void* stream);
+/* The same Adam step / torch.optim.SGD(momentum, dampening 0; train.py:69) with the schedule-driven hyper-parameters in DEVICE memory:
+ * hyper_dev = [step count (1-based, as float; advance it with awr_adam_tick), learning rate], so a captured CUDA graph follows
+ * StepLR / ReduceLROnPlateau (train.py:89-92,157-160) without re-capture.  skip_spans_dev (or NULL): n_skip <= 256 pairs [begin, end)
+ * of flat indices (multiples of 4) that the step leaves untouched -- parameters whose gradient is None in the reference (the
+ * Hourglass skip_layer convs forward never calls, model/hourglass.py:38,45-48), which torch.optim skips.
+ * zero_grad != 0: g is zero-filled once consumed (the next step's weight-gradient kernels accumulate into it), which replaces a separate
+ * 4*n-byte fill per step. */
+int awr_optim_adam(float* p, float* g, float* m, float* v, void* bf16_shadow, long long n, const float* hyper_dev, float beta1,
+                   float beta2, float eps, float weight_decay, float grad_scale, const long long* skip_spans_dev, int n_skip, int zero_grad,
+                   void* stream);
+int awr_optim_sgd(float* p, float* g, float* momentum_buf, void* bf16_shadow, long long n, const float* hyper_dev, float momentum,
+                  float weight_decay, float grad_scale, const long long* skip_spans_dev, int n_skip, int zero_grad, void* stream);
+/* cudaMemsetAsync(p, 0, nbytes) on `stream` (a memset node when captured): the per-step zero fill of the accumulator arena. */
+int awr_memset_zero(void* p, long long nbytes, void* stream);
 int awr_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 
 /* ---- convolutions, CUDA-core fp32-accumulate path (fp32 precision mode; also the 1-channel stem) --------------
@@ -194,8 +216,8 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, 
                         int Cg, int R, int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
 
 /* 1-channel k x k stride-1 'same' stem convolution: x (N,H,W) fp32, w [k*k][Cout] fp32, bias or NULL -> y NHWC.
- * stats (or NULL; k = 5 only): fp32 [2*Cout] += per-channel sum / sum of squares of the stored outputs (BatchNorm statistics). */
-int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, float* stats, int dtype, int N, int H, int W, int Cout, int k,
+ * stats (or NULL; k = 5 only): awr_acc_t[2*Cout] += per-channel sum / sum of squares of the stored outputs (BatchNorm statistics). */
+int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, void* stats, int dtype, int N, int H, int W, int Cout, int k,
                   void* stream);
 /* dW[k*k][Cout] += ..., dbias[Cout] += ... (dbias may be NULL); caller zero-fills. */
 int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int dtype, int N, int H, int W, int Cout, int k,
@@ -205,10 +227,10 @@ int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int 
  * NHWC bf16 activations, bf16 weights (the Adam kernel's shadow copy, same physical order [kh][kw][Cout][Cin]), fp32
  * accumulation in TMEM, operands staged by TMA (shifted boxes = implicit im2col, zero OOB fill = padding).
  * Same argument meaning as awr_conv_simt (w strides select fprop [w_sk==1] or dgrad [w_sn==1]); Ck, Cn multiples of 64,
- * feature-map sides powers of two <= 256, stride 1 or 2.  stats (or NULL): fp32 [2*Cn], the epilogue adds the per-channel sum and
+ * feature-map sides powers of two <= 256, stride 1 or 2.  stats (or NULL): awr_acc_t[2*Cn], the epilogue adds the per-channel sum and
  * sum of squares of the (bf16-rounded) outputs -- the BatchNorm batch statistics -- so no separate reduction pass is needed
  * (caller zero-fills).  Returns AWR_ERR_DRIVER (-3) if the driver cannot encode a tensor map. */
-int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, float* stats, int N, int Hi, int Wi, int Ck, int Ho, int Wo,
+int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, void* stats, int N, int Hi, int Wi, int Ck, int Ho, int Wo,
                 int Cn, int R, int S, int stride, int pad, int transposed, int w_sk, int w_sn, int w_tap, int out_mode, int n_valid,
                 int accumulate, void* stream);
 
@@ -216,16 +238,6 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, flo
  * atomic adds: caller zero-fills).  The contraction runs over pixels; both operands are MN-major TMA boxes of the NHWC tensors. */
 int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
                       int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
-
-/* ---- debug / hardware probes (not on the product path) -------------------------------------------------------------- */
-/* D[128][64] fp32 = A * Bm^T where A is the row-shifted window {r0 + (m/8)*sbo_rows + m%8} of the TMA-loaded smem tile G[rows][64]
- * (bf16, SWIZZLE_128B); probes UMMA descriptor start-address / SBO / base-offset semantics (tools/dbg_umma_window.py). */
-/* MMA issue/execute rate: out_dev[grid] cycles for iters*4 tcgen05.mma (M=128,N,K=16) over nacc accumulators (tools/dbg_umma_rate.py). */
-int awr_debug_umma_rate(unsigned long long* out_dev, int N, int nacc, int iters, int a_rows_shift, int grid, void* stream);
-/* MMA-issuer loop probe: commit / barrier-wait / TMA-fed ring overheads per group of `per` MMAs (tools/dbg_umma_rate.py). */
-int awr_debug_umma_pipe(const void* G, int g_rows, unsigned long long* out_dev, int N, int per, int groups, int mode, int stages,
-                        int tma_rows, int grid, void* stream);
-int awr_debug_umma_window(const void* G, const void* Bm, float* D, int rows, int r0, int sbo_rows, int base_mode, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 def _run(lib, L, fused, dt, dout, act, y, mi, gamma, beta, remask, dy_add, want_dres, dres_add, M, C):
     tdt = torch.float32 if dt == L.F32 else torch.bfloat16
-    dsums = torch.zeros(2 * C, device="cuda")
+    dsums = L.acc_zeros(2 * C, "cuda")            # order-independent accumulators (awr_acc_t)
     dy = dy_add.clone() if dy_add is not None else torch.empty(M, C, device="cuda", dtype=tdt)
     dres = (dres_add.clone() if dres_add is not None else torch.empty(M, C, device="cuda", dtype=tdt)) if want_dres else None
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
@@ -29,7 +29,7 @@ def _run(lib, L, fused, dt, dout, act, y, mi, gamma, beta, remask, dy_add, want_
         L.check(lib.awr_bn_bwd_apply(p(dout), p(a), p(y), p(mi), p(dsums), p(gamma), p(dy), p(dy) if dy_add is not None else None, p(dres),
                                      p(dres) if dres_add is not None else None, p(dg), p(db), p(mb), dt, M, C, 1, L.stream()), "apply")
     torch.cuda.synchronize()
-    return dy, dres, dsums, dg, db
+    return dy, dres, L.acc_to_float(dsums).float(), dg, db
 
 
 @pytest.mark.parametrize("M,C", [(2048, 512), (8192, 256), (32768, 128), (600, 64)])

@@ -60,8 +60,10 @@ def test_conv2d_fprop_dgrad(case):
     ref.backward(gy)
     w_phys = w.permute(2, 3, 0, 1).contiguous().to(torch.bfloat16).cuda()       # [kh][kw][Co][Ci]
     y = torch.full((N, Ho, Ho, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
-    stats = torch.zeros(2 * Co, dtype=torch.float32, device="cuda")
+    from awr_b200 import _lib as L
+    stats = L.acc_zeros(2 * Co, "cuda")
     _conv_tc(_nhwc(x), w_phys, b.cuda(), y, N, H, H, Ci, Ho, Ho, Co, k, s, pad, 0, 1, Ci, Co * Ci, stats=stats)
+    stats = L.acc_to_float(stats)
     got = _from_nhwc(y)
     assert (got - ref.detach()).abs().max().item() < 1e-2 * ref.abs().max().item()
     # fused BatchNorm statistics == per-channel sum / sum of squares of the stored (bf16) output
@@ -99,8 +101,10 @@ def test_conv_transpose2d_fprop_dgrad(case):
     Ho = 2 * H
     w_phys = w.permute(2, 3, 1, 0).contiguous().to(torch.bfloat16).cuda()       # [kh][kw][Co][Ci]
     y = torch.full((N, Ho, Ho, Co), float("nan"), dtype=torch.bfloat16, device="cuda")
-    stats = torch.zeros(2 * Co, dtype=torch.float32, device="cuda")
+    from awr_b200 import _lib as L
+    stats = L.acc_zeros(2 * Co, "cuda")
     _conv_tc(_nhwc(x), w_phys, None, y, N, H, H, Ci, Ho, Ho, Co, 4, 2, 1, 1, 1, Ci, Co * Ci, stats=stats)
+    stats = L.acc_to_float(stats)
     got = _from_nhwc(y)
     assert (got - ref.detach()).abs().max().item() < 1e-2 * ref.abs().max().item()
     s1, s2 = got.double().sum(dim=(0, 2, 3)), (got.double() ** 2).sum(dim=(0, 2, 3))

@@ -20,11 +20,12 @@ def test_stem_conv_with_fused_statistics():
     b = torch.randn(Co, generator=g).cuda()
     ref = F.conv2d(x, w, b, padding=2)
     y = torch.empty(N, H, H, Co, device="cuda")
-    stats = torch.zeros(2 * Co, device="cuda")
+    stats = L.acc_zeros(2 * Co, "cuda")
     w_phys = w.permute(2, 3, 0, 1).contiguous().view(k * k, Co)
     L.check(L.lib().awr_stem_conv(x.data_ptr(), w_phys.data_ptr(), b.data_ptr(), y.data_ptr(), stats.data_ptr(), L.F32, N, H, H, Co, k, L.stream()), "stem")
     torch.cuda.synchronize()
     assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-5, rtol=1e-5)                    # fp32, tolerance 1e-5
+    stats = L.acc_to_float(stats).float()
     assert torch.allclose(stats[:Co], ref.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
     assert torch.allclose(stats[Co:], (ref * ref).sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
 
@@ -50,12 +51,12 @@ def test_bn_relu_maxpool_fwd_and_bwd(k, s, p):
     idx = torch.empty(N, Ho, Ho, C, dtype=torch.uint8, device="cuda")
     mi = torch.empty(2 * C, device="cuda")
     nbt = torch.zeros((), dtype=torch.long, device="cuda")
-    L.check(lib.awr_bn_relu_maxpool_fwd(yn.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(),
+    L.check(lib.awr_bn_relu_maxpool_fwd(yn.data_ptr(), L.acc_from_float(sums).data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(), nbt.data_ptr(),
                                         mi.data_ptr(), out.data_ptr(), idx.data_ptr(), L.F32, N, H, H, C, k, s, p, 0.1, 1e-5, 1, L.stream()), "fwd")
     torch.cuda.synchronize()
     assert torch.allclose(out.permute(0, 3, 1, 2), ref.detach(), atol=1e-5, rtol=1e-5)
     assert nbt.item() == 1 and torch.allclose(rm, 0.1 * y.mean(dim=(0, 2, 3)), atol=1e-6)
-    dsums = torch.zeros(2 * C, device="cuda")
+    dsums = L.acc_zeros(2 * C, "cuda")
     dy = torch.empty_like(yn)
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dpool = _nhwc(dout)
@@ -86,7 +87,7 @@ def test_bn_relu_maxpool3_fwd_bf16_value_and_argmax():
     Ho = (H + 2 * p - k) // s + 1
     out = torch.empty(N, Ho, Ho, C, device="cuda", dtype=torch.bfloat16)
     idx = torch.empty(N, Ho, Ho, C, dtype=torch.uint8, device="cuda")
-    L.check(L.lib().awr_bn_relu_maxpool_fwd(yn.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+    L.check(L.lib().awr_bn_relu_maxpool_fwd(yn.data_ptr(), L.acc_from_float(sums).data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
                                             nbt.data_ptr(), mi.data_ptr(), out.data_ptr(), idx.data_ptr(), L.BF16, N, H, H, C, k, s, p, 0.1, 1e-5, 1,
                                             L.stream()), "fwd")
     torch.cuda.synchronize()

@@ -6,8 +6,7 @@ from awr_b200 import _lib as L
 lib = L.lib()
 fn = lib.awr_debug_conv_profile; fn.argtypes = [C.c_void_p, C.c_int]; fn.restype = C.c_int
 buf = np.zeros(148 * 8, dtype=np.uint64)
-hfn = lib.awr_debug_halo_profile; hfn.argtypes = [C.c_void_p, C.c_int]; hfn.restype = C.c_int
-hbuf = np.zeros(148 * 16, dtype=np.uint64)
+# (the halo-tile kernel has its own event timeline: tools/dbg_halo_timeline.py)
 
 def run(name, N, Ci, Co, H, k, s, pad, transposed=0, mn=0, stats=False, reps=3):
     Ho = (H - 1) * s - 2 * pad + k if transposed else (H + 2 * pad - k) // s + 1
@@ -16,12 +15,12 @@ def run(name, N, Ci, Co, H, k, s, pad, transposed=0, mn=0, stats=False, reps=3):
     if mn:   # dgrad: in has Co channels
         x = torch.randn(N, H, H, Co, device="cuda").bfloat16()
     y = torch.empty(N, Ho, Ho, Ci if mn else Co, device="cuda", dtype=torch.bfloat16)
-    st = torch.zeros(2 * Co, device="cuda") if stats else None
-    fn(buf.ctypes.data, 1); hfn(hbuf.ctypes.data, 1)
+    st = L.acc_zeros(2 * Co, "cuda") if stats else None
+    fn(buf.ctypes.data, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for r in range(reps + 1):
         if r == 1:
-            fn(buf.ctypes.data, 1); hfn(hbuf.ctypes.data, 1); e0.record()
+            fn(buf.ctypes.data, 1); e0.record()
         if not mn:
             L.check(lib.awr_conv_tc(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), None if st is None else st.data_ptr(), N, H, H, Ci, Ho, Ho, Co, k, k, s, pad,
                                     transposed, 1, Ci, Co * Ci, 0, 0, 0, L.stream()), "conv")
@@ -29,15 +28,12 @@ def run(name, N, Ci, Co, H, k, s, pad, transposed=0, mn=0, stats=False, reps=3):
             L.check(lib.awr_conv_tc(x.data_ptr(), w.data_ptr(), None, y.data_ptr(), None, N, H, H, Co, Ho, Ho, Ci, k, k, s, pad,
                                     transposed, Ci, 1, Co * Ci, 0, 0, 0, L.stream()), "conv")
     e1.record(); torch.cuda.synchronize()
-    fn(buf.ctypes.data, 0); hfn(hbuf.ctypes.data, 0)
-    hp = hbuf.reshape(148, 16).astype(np.float64) / reps
-    if hp[:, 7].sum() > 0:
-        m = hp[hp[:, 7] > 0].mean(axis=0)
-        print(f"{name:34s} {1e3 * e0.elapsed_time(e1) / reps:7.1f} us HALO | total {m[7]:8.0f} cyc items {m[8]:.1f} | prod wait h-empty {m[0]:7.0f} b-empty {m[1]:7.0f} | mma wait h-full {m[2]:7.0f} "
-              f"b-full {m[3]:7.0f} tmem {m[4]:7.0f} | epi wait-full {m[5]:7.0f} busy {m[6]:7.0f} (per item {m[6] / max(m[8], 1):6.0f}) | mma issue-block {m[9]:7.0f}")
-        return
+    fn(buf.ctypes.data, 0)
     p = buf.reshape(148, 8).astype(np.float64) / reps
     act = p[:, 5] > 0
+    if not act.any():
+        print(f"{name:34s} {1e3 * e0.elapsed_time(e1) / reps:7.1f} us  (halo-tile kernel: see tools/dbg_halo_timeline.py)")
+        return
     m = p[act].mean(axis=0)
     print(f"{name:34s} {1e3 * e0.elapsed_time(e1) / reps:7.1f} us | total {m[5]:8.0f} cyc  tiles {m[6]:.1f} kiters {m[7]:.0f} | prod wait-empty {m[0]:7.0f}  mma wait-full {m[1]:7.0f} "
           f"wait-tmem {m[2]:7.0f} | epi wait-full {m[3]:7.0f} busy {m[4]:7.0f}  (per tile: epi busy {m[4] / max(m[6], 1):6.0f}, per k-iter total {m[5] / max(m[7], 1):5.0f})")

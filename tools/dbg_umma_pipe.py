@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from awr_b200 import _lib as L
-lib = L.lib()
+import _dbglib
+lib = _dbglib.lib()          # hardware probes live in libawr_b200_debug.so (make debug)
 G = torch.randn(65536, 64, device="cuda").bfloat16()
 def run(N, per, mode, stages, rows, grid=148, groups=2000):
     out = torch.zeros(grid, dtype=torch.int64, device="cuda")

@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from awr_b200 import _lib as L
-lib = L.lib()
+import _dbglib
+lib = _dbglib.lib()          # hardware probes live in libawr_b200_debug.so (make debug)
 rows = 256
 g = torch.Generator().manual_seed(0)
 G = torch.randn(rows, 64, generator=g).bfloat16()

@@ -40,7 +40,7 @@ def conv_step(N, H, C, stats):
     x = torch.randn(N, H, H, C, device=dev).bfloat16()
     w = (torch.randn(3, 3, C, C, device=dev) * 0.05).bfloat16()
     y = torch.empty(N, H, H, C, device=dev, dtype=torch.bfloat16)
-    st = torch.zeros(2 * C, device=dev) if stats else None
+    st = L.acc_zeros(2 * C, dev) if stats else None
     keep = (x, w, y, st)
 
     def step():

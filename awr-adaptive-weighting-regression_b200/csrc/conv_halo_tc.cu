@@ -22,7 +22,9 @@
 //    8 channels -- no separate statistics pass, no shared-memory atomics -- and one fixed-order reduction per CTA feeds the
 //    order-independent global accumulators (AwrAcc, common.cuh): the statistics are bit-reproducible;
 //  * the epilogue works in 64-column halves through a 2 x 16 KB staging area (was 2 x 32 KB), which pays for the deeper rings.
-// Roles: warps 0-7 epilogue (two groups of four, one per sub-tile), warp 8 halo producer, warp 9 MMA issuer, warp 10 weight producer.
+// Roles: warps 0-7 epilogue (two groups of four, one per sub-tile), warp 8 halo producer, warp 10 weight producer, warps 9 / 11 MMA issuers
+// (one per sub-tile: a lone thread needs ~40 cycles per tcgen05.mma it issues plus ~450 per barrier round, tools/dbg_umma_queue.py -- as
+// long as a 48-cycle N=64 MMA takes to execute -- so each sub-tile's accumulator gets its own issuing warp).
 //
 // Handles every unit-stride gather: stride-1 Conv2d fprop/dgrad, ConvTranspose2d(k4,s2,p1) fprop parity classes, stride-2 Conv2d
 // dgrad parity classes, on feature maps >= 16x16 with tap extents <= 2.  Other cases stay on conv_tc_kernel.
@@ -34,7 +36,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 352;                 // 8 epilogue warps (two groups, one per sub-tile) + halo producer warp + MMA issuer warp + weight producer warp
+constexpr int kThreads = 384;                 // 8 epilogue warps (two groups, one per sub-tile) + halo producer + MMA issuer 0 + weight producer + MMA issuer 1
 constexpr int kMaxHaloStages = 3;
 constexpr int kMaxBStages = 10;               // ring depth, or the resident tap count
 constexpr int kStagingBytes = 2 * 128 * 128;  // two epilogue groups x 128 rows x 64 bf16
@@ -102,15 +104,12 @@ struct ItemIter {
   __device__ __forceinline__ void next() { j += step; }
 };
 
-// the 8 MMAs of one tap: two sub-tiles (sub-tile 1 = 8 pixels = 1024 B to the right) x four K=16 steps, sharing the weight tile `bd`
-__device__ __forceinline__ void issue_tap(uint32_t d0, uint32_t d1, uint64_t a0, uint64_t bd, uint32_t bstep, uint32_t idesc, uint32_t acc0) {
-  umma_bf16(d0, a0, bd, idesc, acc0);
-  umma_bf16(d1, a0 + 64, bd, idesc, acc0);
+// the 4 MMAs of one tap for ONE sub-tile: four K=16 steps on the weight tile `bd` (both MMA warps read the same weight tile; sub-tile 1's
+// A window is 8 pixels = 1024 B to the right of sub-tile 0's)
+__device__ __forceinline__ void issue_tap(uint32_t d, uint64_t a0, uint64_t bd, uint32_t bstep, uint32_t idesc, uint32_t acc0) {
+  umma_bf16(d, a0, bd, idesc, acc0);
 #pragma unroll
-  for (int k = 1; k < 4; ++k) {
-    umma_bf16(d0, a0 + 2 * k, bd + k * bstep, idesc, 1u);
-    umma_bf16(d1, a0 + 64 + 2 * k, bd + k * bstep, idesc, 1u);
-  }
+  for (int k = 1; k < 4; ++k) umma_bf16(d, a0 + 2 * k, bd + k * bstep, idesc, 1u);
 }
 
 // NH = Ntile / 64 (64-column halves of the accumulator tile); E = window extent of the tap grid; CL = CTA pairs sharing weight tiles
@@ -142,9 +141,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < p.halo_stages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], CL ? 2 : 1); }     // pair: both MMA warps release a stage
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    // every consumer-side barrier counts BOTH MMA warps (one commit each); in a CTA pair a weight stage is released by all four
+    for (int i = 0; i < p.halo_stages; ++i) { mbar_init(&hfull[i], 1); mbar_init(&hempty[i], 2); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], CL ? 4 : 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 8); }
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(&tmem_base_s, kTmemCols);
@@ -238,13 +238,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.resident) break;                                // weights stay in shared memory: nothing more to load
       }
     }
-  } else if (warp == 9) {
-    // ======================================= MMA issuer =======================================
+  } else if (warp == 9 || warp == 11) {
+    // ======================================= MMA issuers (warp 9: sub-tile 0, warp 11: sub-tile 1) =======================================
+    const int sub = warp == 9 ? 0 : 1;
     const uint32_t idesc = umma_idesc_bf16(128, Ntile, 0, p.b_mn);
     const uint64_t bdesc0 = p.b_mn ? umma_desc_sw128(b_base, 8192, 1024) : umma_desc_sw128(b_base, 16, 1024);
     const uint32_t bstep = p.b_mn ? (2048u >> 4) : (32u >> 4);
     constexpr uint32_t bsstep = (uint32_t)b_bytes >> 4;          // one tile; a ring stage holds a pair (2 * bsstep)
-    const uint64_t adesc0 = umma_desc_sw128(smem_base, 16, (uint32_t)PW * 128u);        // SBO = halo row pitch
+    const uint64_t adesc0 = umma_desc_sw128(smem_base + (uint32_t)sub * 1024u, 16, (uint32_t)PW * 128u);        // SBO = halo row pitch
     const uint32_t hstep = (uint32_t)p.halo_stage_bytes >> 4;
     int hs = 0; uint32_t hph = 0; int bs = 0; uint32_t bph = 0;
     int as = 0; uint32_t aphase = 0;
@@ -254,11 +255,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bool first_item = true;
       for (ItemIter<CL> it(p, rank); it.valid(); it.next()) {
         mbar_wait(&tempty[as], aphase ^ 1u);
-        if (lane == 0) HTL(20);
+        if (lane == 0 && sub == 0) HTL(20);
         tc_fence_after();
         mbar_wait(&hfull[hs], hph);
-        if (lane == 0) HTL(21);
-        const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * Ntile), d1 = d0 + (uint32_t)Ntile;
+        if (lane == 0 && sub == 0) HTL(21);
+        const uint32_t d = tmem_base + (uint32_t)((as * 2 + sub) * Ntile);
         const uint64_t ah = adesc0 + (uint64_t)((uint32_t)hs * hstep);
         if (first_item) {               // the weight tiles are still arriving: tap by tap, as they land
           first_item = false;
@@ -266,7 +267,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int g = 0; g < NT; ++g) {
             if ((g & 1) == 0) mbar_wait(&bfull[g >> 1], 0);
             if (elect_one()) {
-              issue_tap(d0, d1, ah + (uint64_t)(((g / GW) * PW + (g % GW)) * 8), bdesc0 + (uint64_t)(g * bsstep), bstep, idesc, g ? 1u : 0u);
+              issue_tap(d, ah + (uint64_t)(((g / GW) * PW + (g % GW)) * 8), bdesc0 + (uint64_t)(g * bsstep), bstep, idesc, g ? 1u : 0u);
               if (g == NT - 1) { umma_commit(&hempty[hs]); umma_commit(&tfull[as]); }
             }
             __syncwarp();
@@ -274,12 +275,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else if (elect_one()) {
 #pragma unroll
           for (int g = 0; g < NT; ++g)
-            issue_tap(d0, d1, ah + (uint64_t)(((g / GW) * PW + (g % GW)) * 8), bdesc0 + (uint64_t)(g * bsstep), bstep, idesc, g ? 1u : 0u);
+            issue_tap(d, ah + (uint64_t)(((g / GW) * PW + (g % GW)) * 8), bdesc0 + (uint64_t)(g * bsstep), bstep, idesc, g ? 1u : 0u);
           umma_commit(&hempty[hs]);
           umma_commit(&tfull[as]);
         }
         __syncwarp();
-        if (lane == 0) HTL(22);
+        if (lane == 0 && sub == 0) HTL(22);
         if (++hs == p.halo_stages) { hs = 0; hph ^= 1u; }
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
@@ -288,26 +289,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int c = it.j / p.items_m;
         const uint32_t mask = (uint32_t)p.cls[c].mask, last_g = (uint32_t)p.cls[c].last_g;
         mbar_wait(&tempty[as], aphase ^ 1u);
-        if (lane == 0) HTL(20);
+        if (lane == 0 && sub == 0) HTL(20);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(as * 2 * Ntile), d1 = d0 + (uint32_t)Ntile;
+        const uint32_t d = tmem_base + (uint32_t)((as * 2 + sub) * Ntile);
         uint32_t acc = 0;                              // 0 for the first tap of the item, 1 afterwards
         for (int kc = 0; kc < p.kblocks && mask != 0; ++kc) {
           mbar_wait(&hfull[hs], hph);
-          if (lane == 0) HTL(21);
+          if (lane == 0 && sub == 0) HTL(21);
           const uint64_t ah = adesc0 + (uint64_t)((uint32_t)hs * hstep);
-          // grid positions in pairs: up to 16 MMAs per elected block, A-window offsets are immediates
+          // grid positions in pairs: up to 8 MMAs per warp and elected block, A-window offsets are immediates
 #pragma unroll
           for (int g = 0; g < NT; g += 2) {
             const bool t0 = (mask >> g) & 1u, t1 = (g + 1 < NT) && ((mask >> (g + 1)) & 1u);
             if (!(t0 || t1)) continue;
-            if (lane == 0) HTL(23);
+            if (lane == 0 && sub == 0) HTL(23);
             mbar_wait(&bfull[bs], bph);
-            if (lane == 0) HTL(24);
+            if (lane == 0 && sub == 0) HTL(24);
             if (elect_one()) {
               const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)bs * 2u * bsstep);
-              if (t0) issue_tap(d0, d1, ah + (uint64_t)(((g / GW) * PW + (g % GW)) * 8), bd, bstep, idesc, acc);
-              if (t1) issue_tap(d0, d1, ah + (uint64_t)((((g + 1) / GW) * PW + ((g + 1) % GW)) * 8), bd + (uint64_t)(t0 ? bsstep : 0u), bstep, idesc,
+              if (t0) issue_tap(d, ah + (uint64_t)(((g / GW) * PW + (g % GW)) * 8), bd, bstep, idesc, acc);
+              if (t1) issue_tap(d, ah + (uint64_t)((((g + 1) / GW) * PW + ((g + 1) % GW)) * 8), bd + (uint64_t)(t0 ? bsstep : 0u), bstep, idesc,
                                 t0 ? 1u : acc);
               if (CL) umma_commit_mc(&bempty[bs], (uint16_t)3); else umma_commit(&bempty[bs]);
               if ((uint32_t)g == last_g || (uint32_t)(g + 1) == last_g) umma_commit(&hempty[hs]);
@@ -323,7 +324,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else mbar_arrive(&tfull[as]);
         }
         __syncwarp();
-        if (lane == 0) HTL(22);
+        if (lane == 0 && sub == 0) HTL(22);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }

@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(128, 1) umma_rate2_kernel(unsigned long long* 
           umma_bf16(tmem + (uint32_t)N, a1 + 2 * k, bd + 2 * k, idesc, 1u);
         }
       }
+      const long long t1 = clock64();                    // issue done (the MMAs may still be queued / executing)
       umma_commit(&done_bar);
+      out[gridDim.x + blockIdx.x] = (unsigned long long)(t1 - t0);
     }
     __syncwarp();
     mbar_wait(&done_bar, 0);

@@ -9,7 +9,10 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("AWR_B200_LIB") or os.path.join(_HERE, "libawr_b200.so")      # override: debug builds (make PROFILE=1)
+# AWR_B200_DETERMINISTIC=1 selects the bit-reproducible build (make DET=1: order-independent accumulators for every sum several CTAs
+# share; ~3 % slower); AWR_B200_LIB overrides the path outright (debug builds, make PROFILE=1)
+LIB_PATH = os.environ.get("AWR_B200_LIB") or os.path.join(
+    _HERE, "libawr_b200_det.so" if os.environ.get("AWR_B200_DETERMINISTIC") == "1" else "libawr_b200.so")
 
 F32, BF16 = 0, 1
 HUBER_MAX_BLOCKS = 1184
@@ -69,18 +72,30 @@ def acc_zeros(n, device):
     return torch.zeros(n, 2, dtype=torch.int64, device=device)
 
 
+def deterministic():
+    """True when the loaded library is the bit-reproducible build (slots hold two-limb integers; the default build keeps one fp32
+    sum in a slot's first four bytes)."""
+    return bool(lib().awr_deterministic())
+
+
 def acc_to_float(t):
     """awr_acc_t[n] -> float64[n]."""
-    t = t.view(-1, 2)
-    return t[:, 0].double() * 2.0 ** -24 + t[:, 1].double() * 2.0 ** -72
+    t = t.contiguous().view(-1, 2)
+    if deterministic():
+        return t[:, 0].double() * 2.0 ** -24 + t[:, 1].double() * 2.0 ** -72
+    return t.view(torch.float32).view(-1, 4)[:, 0].double()
 
 
 def acc_from_float(v):
     """float[n] -> awr_acc_t[n] (for callers that computed the sums themselves)."""
     v = v.double().flatten()
-    hi = torch.round(v * 2.0 ** 24)
-    lo = torch.round((v - hi * 2.0 ** -24) * 2.0 ** 72)
-    return torch.stack([hi.long(), lo.long()], dim=1).contiguous()
+    if deterministic():
+        hi = torch.round(v * 2.0 ** 24)
+        lo = torch.round((v - hi * 2.0 ** -24) * 2.0 ** 72)
+        return torch.stack([hi.long(), lo.long()], dim=1).contiguous()
+    out = torch.zeros(v.numel(), 4, dtype=torch.float32, device=v.device)
+    out[:, 0] = v.float()
+    return out.view(torch.int64).view(-1, 2).contiguous()
 
 
 def check(rc: int, what: str):

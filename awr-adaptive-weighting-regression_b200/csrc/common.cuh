@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+int awr_sm_budget();          // api.cu: grid cap of the persistent tensor-core kernels (148 unless the trainer reserves SMs for NCCL)
+
 #define AWR_OK 0
 #define AWR_ERR_BAD_ARG (-1)
 #define AWR_ERR_UNSUPPORTED (-2)
@@ -55,7 +57,14 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
 // (|p| < 2^39; bits below 2^-72 are rounded per addend), integer addition is associative, so the total does not depend on the
 // order in which CTAs arrive -- together with fixed per-CTA work assignment this makes the statistics bit-reproducible run to run,
 // which fp32 atomicAdd is not (the reference is bit-deterministic on CPU).  Layout: AwrAcc[n] = n x 16 bytes, zero-filled by the caller.
+//
+// Two builds share this 16-byte slot layout (and so one ABI): libawr_b200_det.so (-DAWR_DETERMINISTIC, `make DET=1`) uses the two-limb
+// integers; the default libawr_b200.so keeps ONE fp32 atomic per contribution in the slot's first four bytes -- the integer pairs cost
+// ~60 us per 2 ms training step (two 64-bit atomics per value, 592-way contended, in every BatchNorm reduction).  Weight gradients follow
+// the same switch through GradT / grad_add: fp32 atomics into the flat gradient buffer, or AwrAcc slots that awr_grad_acc_finalize folds
+// into it.
 struct __align__(16) AwrAcc { long long hi, lo; };
+#ifdef AWR_DETERMINISTIC
 __device__ __forceinline__ void acc_add(AwrAcc* dst, float p) {
   const long long a = __float2ll_rn(p * 0x1p24f);
   const float r = fmaf(-__ll2float_rn(a), 0x1p-24f, p);          // exact remainder, |r| <= 2^-25
@@ -64,6 +73,15 @@ __device__ __forceinline__ void acc_add(AwrAcc* dst, float p) {
   if (b) atomicAdd(reinterpret_cast<unsigned long long*>(&dst->lo), (unsigned long long)b);
 }
 __device__ __forceinline__ float acc_value(longlong2 v) { return fmaf(__ll2float_rn(v.y), 0x1p-72f, __ll2float_rn(v.x) * 0x1p-24f); }
+typedef AwrAcc GradT;
+#else
+__device__ __forceinline__ void acc_add(AwrAcc* dst, float p) { atomicAdd(reinterpret_cast<float*>(dst), p); }
+__device__ __forceinline__ float acc_value(longlong2 v) { return __int_as_float((int)(unsigned)(v.x & 0xffffffffll)); }
+typedef float GradT;
+#endif
+// one contribution to a weight-gradient element shared by several CTAs (split-K)
+__device__ __forceinline__ void grad_add(float* p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void grad_add(AwrAcc* p, float v) { acc_add(p, v); }
 // eight consecutive accumulators -> floats: the eight 16-byte loads are issued together, then converted (32 registers in flight)
 __device__ __forceinline__ void acc_get8(const AwrAcc* __restrict__ src, float (&out)[8]) {
   longlong2 r[8];

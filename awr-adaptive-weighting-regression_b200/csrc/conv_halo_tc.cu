@@ -617,11 +617,12 @@ int conv_halo_launch(const ConvGeom& g, const void* in, const void* w, const flo
   const bool pair = env_pair && (p.items_m % 2 == 0) && total >= 2 * p.tiles_c;
   int grid;
   if (pair) {
-    int ncl = (int)(total / 2 < 74 ? total / 2 : 74);
+    const int cap = awr_sm_budget() / 2;
+    int ncl = (int)(total / 2 < cap ? total / 2 : cap);
     ncl -= ncl % p.tiles_c;
     grid = 2 * ncl;
   } else {
-    grid = (int)(total < 148 ? total : 148);
+    grid = (int)(total < awr_sm_budget() ? total : awr_sm_budget());
     grid -= grid % p.tiles_c;
   }
   if (grid < p.tiles_c) return AWR_ERR_UNSUPPORTED;

@@ -141,7 +141,7 @@ struct WgradP {
 };
 // dW[tap][i*s_p + j*s_g] += sum_{coarse pixel q} P[q, i] * G[q*stride - pad + tap, j]
 template <typename T>
-__global__ void __launch_bounds__(256) conv_wgrad_kernel(const T* __restrict__ Pt, const T* __restrict__ Gt, float* __restrict__ dW, WgradP p) {
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const T* __restrict__ Pt, const T* __restrict__ Gt, GradT* __restrict__ dW, WgradP p) {
   pdl_entry();
   __shared__ __align__(16) float Ps[TK][LD];
   __shared__ __align__(16) float Gs[TK][LD];
@@ -180,12 +180,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const T* __restrict__ P
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
     }
   }
-  float* dst = dW + (long long)blockIdx.y * p.w_tap;
+  GradT* dst = dW + (long long)blockIdx.y * p.w_tap;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      atomicAdd(dst + (long long)(i0 + ty * 4 + i) * p.s_p + (long long)(j0 + tx * 4 + j) * p.s_g, acc[i][j]);
+      grad_add(dst + (long long)(i0 + ty * 4 + i) * p.s_p + (long long)(j0 + tx * 4 + j) * p.s_g, acc[i][j]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 
 // dW[tap][co] += sum_pix dy[pix,co] * x[pix + tap];  dbias[co] += sum_pix dy[pix,co]
 template <typename T>
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
-                                                         float* __restrict__ dbias, int N, int H, int W, int Cout, int k, int pix_per_block) {
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, GradT* __restrict__ dW,
+                                                         GradT* __restrict__ dbias, int N, int H, int W, int Cout, int k, int pix_per_block) {
   pdl_entry();
   const int co = threadIdx.x % Cout, tg = threadIdx.x / Cout, ngroups = blockDim.x / Cout;
   const int pad = k / 2, taps = k * k;
@@ -254,17 +254,17 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const int tap = tg + a * ngroups;
-    if (tap < taps) atomicAdd(dW + tap * Cout + co, acc[a]);
+    if (tap < taps) grad_add(dW + tap * Cout + co, acc[a]);
   }
-  if (tg == 0 && dbias) atomicAdd(dbias + co, bsum);
+  if (tg == 0 && dbias) grad_add(dbias + co, bsum);
 }
 
 // Register-tiled stem weight gradient (K x K taps, 1 input channel): block = one image x 8-row band, 4 thread groups x Cout=64
 // channels; each thread keeps all K*K tap accumulators for its channel and walks 8-pixel row segments so every x value
 // fetched from the smem halo tile feeds K FMAs.  One atomicAdd per (tap, channel) per block.
 template <typename T, int K>
-__global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
-                                                               float* __restrict__ dbias, int N, int H, int W) {
+__global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __restrict__ x, const T* __restrict__ dy, GradT* __restrict__ dW,
+                                                               GradT* __restrict__ dbias, int N, int H, int W) {
   pdl_entry();
   constexpr int RB = 8, CO = 64, PADK = K / 2, XS = 8 + K - 1;
   extern __shared__ __align__(16) float sm[];
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_tiled_kernel(const float* __re
     float v = 0.f;
 #pragma unroll
     for (int g2 = 0; g2 < 4; ++g2) v += red[(g2 * (K * K + 1) + t) * CO + co];
-    if (t < K * K) atomicAdd(dW + t * CO + co, v);
-    else if (dbias) atomicAdd(dbias + co, v);
+    if (t < K * K) grad_add(dW + t * CO + co, v);
+    else if (dbias) grad_add(dbias + co, v);
   }
 }
 
@@ -329,8 +329,8 @@ template <> struct Pair2<bf16> {
   static __device__ __forceinline__ float2 load(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
 };
 template <typename T, int K>
-__global__ void __launch_bounds__(256) stem_wgrad_pair_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dW,
-                                                              float* __restrict__ dbias, int N, int H, int W) {
+__global__ void __launch_bounds__(256) stem_wgrad_pair_kernel(const float* __restrict__ x, const T* __restrict__ dy, GradT* __restrict__ dW,
+                                                              GradT* __restrict__ dbias, int N, int H, int W) {
   pdl_entry();
   constexpr int RB = 8, CO = 64, PADK = K / 2, XS = 12, KK = K * K, HALF = (KK + 2) / 2;     // 26 values (taps + bias) in two rounds of 13
   static_assert(K == 5, "row loader is written for the 5x5 stem");
@@ -394,8 +394,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_pair_kernel(const float* __res
       float v = 0.f;
 #pragma unroll
       for (int g2 = 0; g2 < 8; ++g2) v += red[(g2 * HALF + tt) * CO + co];
-      if (t < KK) atomicAdd(dW + t * CO + co, v);
-      else if (dbias) atomicAdd(dbias + co, v);
+      if (t < KK) grad_add(dW + t * CO + co, v);
+      else if (dbias) grad_add(dbias + co, v);
     }
   }
 }
@@ -527,7 +527,7 @@ int awr_conv_simt(const void* in, const float* w, const float* bias, void* out, 
   return AWR_OK;
 }
 
-int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, int dtype, int N, int Hc, int Wc, int Cp, int Hf, int Wf,
+int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, void* dW, int dtype, int N, int Hc, int Wc, int Cp, int Hf, int Wf,
                         int Cg, int R, int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream) {
   AWR_HOST_CHECK(pointwise && gathered && dW && N > 0 && Cp % TM == 0 && Cg % TN == 0);
   const long long Q = (long long)N * Hc * Wc;
@@ -538,7 +538,7 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, 
   if (ksplit < 1) ksplit = 1;
   WgradP p{N, Hc, Wc, Cp, Hf, Wf, Cg, R, S, stride, pad, s_p, s_g, w_tap, ksplit};
   dim3 grid((Cp / TM) * (Cg / TN), R * S, ksplit);
-  DISPATCH_T(dtype, launch_pdl(conv_wgrad_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)pointwise, (const T*)gathered, dW, p));
+  DISPATCH_T(dtype, launch_pdl(conv_wgrad_kernel<T>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const T*)pointwise, (const T*)gathered, reinterpret_cast<GradT*>(dW), p));
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }
@@ -566,7 +566,7 @@ int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, vo
   return AWR_OK;
 }
 
-int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int dtype, int N, int H, int W, int Cout, int k,
+int awr_stem_wgrad(const float* x, const void* dy, void* dW, void* dbias, int dtype, int N, int H, int W, int Cout, int k,
                    void* stream) {
   AWR_HOST_CHECK(x && dy && dW && N > 0 && (Cout == 64 || Cout == 128 || Cout == 256) && k % 2 == 1 && k <= 7);
   const long long P = (long long)N * H * W;
@@ -579,16 +579,16 @@ int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int 
     static const bool old_kernel = [] { const char* e = getenv("AWR_STEM_WGRAD"); return e && e[0] == 'o'; }();       // AWR_STEM_WGRAD=old
     if (!old_kernel) {
       const size_t smem2 = ((size_t)12 * pitch + 8 * 13 * 64) * sizeof(float);
-      DISPATCH_T(dtype, launch_pdl(stem_wgrad_pair_kernel<T, 5>, dim3(N * (H / 8)), dim3(256), smem2, (cudaStream_t)stream, x, (const T*)dy, dW, dbias, N, H, W));
+      DISPATCH_T(dtype, launch_pdl(stem_wgrad_pair_kernel<T, 5>, dim3(N * (H / 8)), dim3(256), smem2, (cudaStream_t)stream, x, (const T*)dy, reinterpret_cast<GradT*>(dW), reinterpret_cast<GradT*>(dbias), N, H, W));
       AWR_LAUNCH_CHECK();
       return AWR_OK;
     }
     const size_t smem = ((size_t)12 * pitch + 4 * 26 * 64) * sizeof(float);
-    DISPATCH_T(dtype, launch_pdl(stem_wgrad_tiled_kernel<T, 5>, dim3(N * (H / 8)), dim3(256), smem, (cudaStream_t)stream, x, (const T*)dy, dW, dbias, N, H, W));
+    DISPATCH_T(dtype, launch_pdl(stem_wgrad_tiled_kernel<T, 5>, dim3(N * (H / 8)), dim3(256), smem, (cudaStream_t)stream, x, (const T*)dy, reinterpret_cast<GradT*>(dW), reinterpret_cast<GradT*>(dbias), N, H, W));
     AWR_LAUNCH_CHECK();
     return AWR_OK;
   }
-  DISPATCH_T(dtype, launch_pdl(stem_wgrad_kernel<T>, dim3((int)((P + ppb - 1) / ppb)), dim3(256), 0, (cudaStream_t)stream, x, (const T*)dy, dW, dbias, N, H,
+  DISPATCH_T(dtype, launch_pdl(stem_wgrad_kernel<T>, dim3((int)((P + ppb - 1) / ppb)), dim3(256), 0, (cudaStream_t)stream, x, (const T*)dy, reinterpret_cast<GradT*>(dW), reinterpret_cast<GradT*>(dbias), N, H,
                                                                                                       W, Cout, k, ppb));
   AWR_LAUNCH_CHECK();
   return AWR_OK;

@@ -397,7 +397,7 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, voi
     attr_set = true;
   }
   const int total_tiles = p.nclasses * p.tiles_m * p.tiles_c;
-  int sms = 148;
+  int sms = awr_sm_budget();
   int grid = total_tiles < sms ? total_tiles : sms;
   if (launch_pdl(conv_tc_kernel, dim3(grid), dim3(kThreads), smem, (cudaStream_t)stream, tmA, tmB, bias, out, reinterpret_cast<AwrAcc*>(stats), p) != cudaSuccess) return (int)cudaGetLastError();
   AWR_LAUNCH_CHECK();

@@ -1345,6 +1345,20 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
   }
 }
+// deterministic build: weight-gradient accumulator slots -> flat fp32 gradient buffer (added: BatchNorm / bias gradients are written there
+// directly), slots re-zeroed for the next step
+__global__ void __launch_bounds__(kEwThreads) grad_acc_finalize_kernel(AwrAcc* __restrict__ acc, float* __restrict__ grads, long long n) {
+  pdl_entry();
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < n; i += stride) {
+    const longlong2 v = *reinterpret_cast<const longlong2*>(acc + i);
+    if (v.x | v.y) {
+      grads[i] += acc_value(v);
+      *reinterpret_cast<longlong2*>(acc + i) = make_longlong2(0ll, 0ll);
+    }
+  }
+}
+
 __global__ void adam_tick_kernel(float* step_dev) {
   pdl_entry(); step_dev[0] += 1.f; }
 
@@ -1714,6 +1728,13 @@ int awr_optim_sgd(float* p, float* g, float* momentum_buf, void* bf16_shadow, lo
   AWR_HOST_CHECK(p && g && momentum_buf && hyper_dev && n > 0 && n_skip >= 0 && n_skip <= 256 && (n_skip == 0 || skip_spans_dev));
   launch_pdl(optim_kernel<false>, dim3(ew_blocks((n + 3) / 4, 2)), dim3(kEwThreads), 0, (cudaStream_t)stream, p, g, momentum_buf, (float*)nullptr,
              (bf16*)bf16_shadow, n, hyper_dev, momentum, 0.f, 0.f, weight_decay, grad_scale, skip_spans_dev, n_skip, zero_grad);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+int awr_grad_acc_finalize(void* acc, float* grads, long long n, void* stream) {
+  AWR_HOST_CHECK(acc && grads && n > 0);
+  launch_pdl(grad_acc_finalize_kernel, dim3(ew_blocks(n, 4)), dim3(kEwThreads), 0, (cudaStream_t)stream, (AwrAcc*)acc, grads, n);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

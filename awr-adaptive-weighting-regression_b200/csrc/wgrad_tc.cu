@@ -33,6 +33,8 @@ constexpr int kMaxGroups = 9;
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// deterministic build: four order-independent accumulator slots instead of one vector reduction
+__device__ __forceinline__ void red_add_v4(AwrAcc* addr, float4 v) { acc_add(addr, v.x); acc_add(addr + 1, v.y); acc_add(addr + 2, v.z); acc_add(addr + 3, v.w); }
 
 struct MTile {
   int tap[2];            // weight tap of each 64-row block
@@ -56,7 +58,7 @@ struct WgradParams {
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1, const __grid_constant__ CUtensorMap tmG2,
-                const __grid_constant__ CUtensorMap tmG3, const __grid_constant__ CUtensorMap tmP, float* __restrict__ dW,
+                const __grid_constant__ CUtensorMap tmG3, const __grid_constant__ CUtensorMap tmP, GradT* __restrict__ dW,
                 const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();                 // the next kernel may start its prologue while this grid runs
@@ -169,7 +171,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
           __syncwarp();
           const int r0 = q * 32, bk = r0 >> 6;                    // the warp's 32 rows lie inside one 64-row block
           if (bk == 0 || T.valid1) {
-            float* wbase = dW + (size_t)T.tap[bk] * p.w_tap + (size_t)(cg0 + T.ch[bk] + (r0 & 63)) * p.s_g + (size_t)(nt * p.Ntile + ch) * p.s_p;
+            GradT* wbase = dW + (size_t)T.tap[bk] * p.w_tap + (size_t)(cg0 + T.ch[bk] + (r0 & 63)) * p.s_g + (size_t)(nt * p.Ntile + ch) * p.s_p;
             if (p.s_p == 1) {
               // columns contiguous (ConvTranspose2d layout): lane -> (row rr0 + lane/8, cols 4*(lane%8)..+3), 8 iterations of 4 rows
               const int cq = (lane & 7) * 4, rsub = lane >> 3;
@@ -204,7 +206,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant_
 
 extern "C" {
 
-int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
+int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, void* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
                       int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream) {
   AWR_HOST_CHECK(pointwise && gathered && dW && N > 0 && Cp % 64 == 0 && Cg % 64 == 0 && (Cg == 64 || Cg % 128 == 0));
   AWR_HOST_CHECK(R > 0 && S > 0 && R * S <= 16 && (stride == 1 || stride == 2));
@@ -319,7 +321,7 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
 
   const int base_items = ng * p.cg_blocks * p.tiles_n;
-  int ksplit = 148 / base_items;                       // whole waves: never more CTAs than SMs unless the base grid already exceeds them
+  int ksplit = awr_sm_budget() / base_items;                       // whole waves: never more CTAs than SMs unless the base grid already exceeds them
   if (ksplit < 1) ksplit = 1;
   if (ksplit > p.pix_blocks) ksplit = p.pix_blocks;
   p.ksplit = ksplit;
@@ -330,7 +332,7 @@ int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, in
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  if (launch_pdl(wgrad_tc_kernel, dim3(base_items * ksplit), dim3(kThreads), smem, (cudaStream_t)stream, tmG[0], tmG[1], tmG[2], tmG[3], tmP, dW, p) != cudaSuccess) return (int)cudaGetLastError();
+  if (launch_pdl(wgrad_tc_kernel, dim3(base_items * ksplit), dim3(kThreads), smem, (cudaStream_t)stream, tmG[0], tmG[1], tmG[2], tmG[3], tmP, reinterpret_cast<GradT*>(dW), p) != cudaSuccess) return (int)cudaGetLastError();
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -18,6 +18,10 @@ def init_from_env(backend=None, device=None):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
+            # the gradient all-reduce overlaps the tail of backward: keep NCCL to the SMs the trainer leaves free for it
+            # (FusedTrainer lowers the conv grids by AWR_B200_NCCL_SMS while a bucket is in flight)
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("AWR_B200_NCCL_SMS", "16"))
         kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
         dist.init_process_group(backend, **kw)
     return rank, local, world

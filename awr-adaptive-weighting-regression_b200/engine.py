@@ -274,6 +274,20 @@ class Plan:
             names += [g + ".weight", g + ".bias"]
         return names
 
+    def trained_param_names(self):
+        """Canonical parameter names some op of this plan reads (and, in training, writes a gradient for).  The rest -- Hourglass
+        skip_layer convs of equal-width Residual blocks (hourglass.py:38,45-48) -- have grad None in the reference."""
+        lay = self.store.layout
+        spans = []
+        for op in self.ops:
+            for n in self._op_param_names(op):
+                if n in lay.groups:
+                    off, shp = lay.groups[n]
+                    spans.append((off, off + int(math.prod(shp))))
+                elif n in lay.specs:
+                    spans.append((lay.specs[n].offset, lay.specs[n].offset + lay.specs[n].numel))
+        return [n for n in lay.order if any(a <= lay.specs[n].offset < b for a, b in spans)]
+
     def _find_bwd_split(self, marks):
         """Early gradient bucket for overlapping the data-parallel all-reduce with the rest of backward: the latest ops (head, deconvs,
         last stage) hold most parameters and finish their gradients first.  Picks the op suffix whose parameters are a contiguous tail
@@ -344,6 +358,16 @@ class Plan:
     def G(self, name):
         return self.store.layout.phys(self.store.grads, name)
 
+    def GW(self, name):
+        """Weight-gradient target of a wgrad kernel: the fp32 gradient view, or (bit-reproducible build) the address of the same
+        element range in the accumulator-slot buffer."""
+        acc = self.store.grads_acc
+        if acc is None:
+            return self.G(name)
+        lay = self.store.layout
+        off = lay.groups[name][0] if name in lay.groups else lay.specs[name].offset
+        return acc.data_ptr() + 16 * off
+
     def W16(self, name):
         return self.store.layout.phys(self.store.shadow, name)
 
@@ -366,15 +390,23 @@ class Plan:
         if side is None:
             for f in self.bwd[lo:hi]:
                 f(s)
-            return
-        main = torch.cuda.current_stream()
-        for f, on_side in list(zip(self.bwd, self.bwd_side))[lo:hi]:
-            if on_side:
-                side.wait_stream(main)
-                f(side.cuda_stream)
-            else:
-                f(s)
-        main.wait_stream(side)
+        else:
+            main = torch.cuda.current_stream()
+            for f, on_side in list(zip(self.bwd, self.bwd_side))[lo:hi]:
+                if on_side:
+                    side.wait_stream(main)
+                    f(side.cuda_stream)
+                else:
+                    f(s)
+            main.wait_stream(side)
+        acc = self.store.grads_acc
+        if acc is not None:
+            # bit-reproducible build: fold the accumulator slots of the gradients that are final now into the fp32 buffer
+            n = self.store.grads.numel()
+            a, b = 0, n
+            if part is not None and self.bwd_split is not None:
+                a, b = (self.bwd_split[1], n) if part == 0 else (0, self.bwd_split[1])
+            L.check(self.lib.awr_grad_acc_finalize(acc.data_ptr() + 16 * a, self.store.grads.data_ptr() + 4 * a, b - a, s), "awr_grad_acc_finalize")
 
     # ---- ops ------------------------------------------------------------------------------------------
     def stem(self, wname, bname, Cout, k):
@@ -521,7 +553,7 @@ class _Stem(_Op):
         pl = self.plan
         if not self.y.gw:
             return
-        pl.call(pl.bwd, "awr_stem_wgrad", pl.img, self.y.grad(), pl.G(self.wname), pl.G(self.bname) if self.bname else None,
+        pl.call(pl.bwd, "awr_stem_wgrad", pl.img, self.y.grad(), pl.GW(self.wname), pl.GW(self.bname) if self.bname else None,
                 pl.dt, pl.B, pl.H, pl.H, self.y.C, self.k)
 
 
@@ -560,7 +592,7 @@ class _Conv(_Op):
         if not y.gw:
             return
         dy = y.grad()
-        gW = pl.G(self.wname)
+        gW = pl.GW(self.wname)
         if pl.tc:
             if not self.transposed:
                 pl.call(pl.bwd, "awr_conv_wgrad_tc", dy, x.t, gW, x.N, y.H, y.W, self.Cout, x.H, x.W, self.Cin, self.k, self.k, self.stride,
@@ -809,7 +841,7 @@ class _Head(_Op):
                 pl.call(pl.bwd, "awr_nchw_to_nhwc", self.dpred, d, pl.dt, x.N, 4 * J, HC, P)
         g = self.gname
         if pl.tc:
-            pl.call(pl.bwd, "awr_conv_wgrad_tc", d, x.t, pl.G(g + ".weight"), x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1, HC * x.C,
+            pl.call(pl.bwd, "awr_conv_wgrad_tc", d, x.t, pl.GW(g + ".weight"), x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1, HC * x.C,
                     flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
             pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, HC, pl.arena(ACC * HC), 0, pl.G(g + ".bias"), pl.arena(1))
 
@@ -818,7 +850,7 @@ class _Head(_Op):
                         x.C, 1, HC * x.C, 0, 0, int(acc), flops=2 * x.M * x.C * 4 * J, tag="conv_dgrad")
             _contribute(pl, x, emit_tc)
             return
-        pl.call(pl.bwd, "awr_conv_wgrad_simt", d, x.t, pl.G(g + ".weight"), pl.dt, x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1,
+        pl.call(pl.bwd, "awr_conv_wgrad_simt", d, x.t, pl.GW(g + ".weight"), pl.dt, x.N, x.H, x.W, HC, x.H, x.W, x.C, 1, 1, 1, 0, x.C, 1,
                 HC * x.C, flops=2 * x.M * x.C * 4 * J, tag="conv_wgrad")
         pl.call(pl.bwd, "awr_channel_stats", d, pl.dt, x.M, HC, pl.arena(ACC * HC), 0, pl.G(g + ".bias"), pl.arena(1))
 

@@ -27,6 +27,9 @@ class ParamStore:
         self.params = torch.zeros(n, dtype=torch.float32, device=device)
         self.grads = torch.zeros(n, dtype=torch.float32, device=device)
         self.shadow = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        # bit-reproducible build: the weight-gradient kernels accumulate into 16-byte order-independent slots (same element offsets as
+        # `grads`), folded into `grads` at the end of backward
+        self.grads_acc = torch.zeros(n, 2, dtype=torch.int64, device=device) if L.deterministic() else None
         self.buffers = {}
         self.shadow_version = -1
 
@@ -72,6 +75,9 @@ class AWRBackbone(nn.Module):
             _get_or_make(self, path).register_buffer(leaf, init)
         # parameter order == module-tree traversal order == the reference's parameters() order
         object.__setattr__(self, "_pnames", [k for k, _ in self.named_parameters()])
+        object.__setattr__(self, "_params_dirty", False)
+        # a load_state_dict() after a FusedTrainer was built must reach the trainer's bf16 weight shadow: flag it, the trainer refreshes
+        self.register_load_state_dict_post_hook(lambda module, incompatible: object.__setattr__(module, "_params_dirty", True))
 
     # ---- storage management ---------------------------------------------------------------------------
     def _params_by_name(self):

@@ -10,7 +10,10 @@ coordinate grid and the loss temporaries of the reference are never materialised
 
 Semantics kept from train.py: loss = coord_weight*SmoothL1(uvd, jt) + dense_weight*SmoothL1(pred, joint2offset(jt))
 (:119-120); for 'hourglass_N' only the last stack is supervised (:116-121 overwrite `loss`); Adam(lr, betas
-(0.9,0.999), eps 1e-8, weight_decay) (:67); BN statistics are per replica (the reference has no SyncBN).
+(0.9,0.999), eps 1e-8, weight_decay) (:67) or SGD(momentum 0.9) (:69); parameters whose gradient is None in the reference
+(Hourglass skip_layer convs that forward never calls) are not stepped, as torch.optim skips them; BN statistics are per
+replica (the reference has no SyncBN).  The learning rate lives in device memory, so StepLR / ReduceLROnPlateau
+(awr_b200.optim, train.py:89-92,157-160) drive the captured graph without re-capture.
 """
 import os
 
@@ -23,9 +26,13 @@ from .modules import AWRBackbone
 
 class FusedTrainer:
     def __init__(self, module: AWRBackbone, batch_size, img_size, kernel_size, coord_weight=1.0, dense_weight=1.0, lr=1e-3,
-                 betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1, use_graph=True, process_group=None, all_stacks=False):
+                 betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1, use_graph=True, process_group=None, all_stacks=False,
+                 optimizer="adam", momentum=0.9, keep_grads=False):
         """all_stacks (hourglass_N, N > 1): supervise every stack and sum the per-stack losses (test.py:74-80); the default keeps
-        train.py:116-121's behaviour, where only the last stack's loss survives the loop."""
+        train.py:116-121's behaviour, where only the last stack's loss survives the loop.
+        optimizer: 'adam' (train.py:67) | 'sgd' (momentum `momentum`, train.py:69).
+        keep_grads: leave the step's gradients in store.grads (tests, inspection); by default the optimizer kernel zero-fills the
+        buffer once it has consumed it, which replaces a separate 4*n-byte fill per step."""
         if not isinstance(module, AWRBackbone):
             raise TypeError("FusedTrainer drives awr_b200 backbones (get_deconv_net / PoseNet)")
         self.module = module
@@ -33,6 +40,9 @@ class FusedTrainer:
         self.B, self.H = int(batch_size), int(img_size)
         self.ks, self.cw, self.dw = float(kernel_size), float(coord_weight), float(dense_weight)
         self.lr, self.betas, self.eps, self.wd = float(lr), betas, float(eps), float(weight_decay)
+        if optimizer not in ("adam", "sgd"):
+            raise ValueError("optimizer must be 'adam' or 'sgd' (train.py:66-69)")
+        self.optimizer, self.momentum, self.keep_grads = optimizer, float(momentum), bool(keep_grads)
         self.world, self.pg = int(world_size), process_group
         self.store = module.store()
         self.plan = module.plan(self.B, self.H, True)
@@ -45,9 +55,24 @@ class FusedTrainer:
         self.head = self.plan.heads[-1]
         self.F = self.head.pred.shape[-1]
         n = self.store.params.numel()
-        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)            # Adam exp_avg / SGD momentum buffer
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev) if optimizer == "adam" else None
+        self.hyper = torch.tensor([0.0, self.lr], dtype=torch.float32, device=dev)      # [step count, learning rate]: read by the optimizer kernel
+        self.step_dev = self.hyper[:1]
+        # parameters no launch of the backward plan writes a gradient for (reference: grad None -> torch.optim skips them)
+        lay = self.store.layout
+        trained = set(self.plan.trained_param_names())
+        self.unused_params = [nm for nm in lay.order if nm not in trained]
+        merged = []
+        for a, b in sorted((lay.specs[nm].offset, lay.specs[nm].offset + (lay.specs[nm].numel + 63) // 64 * 64) for nm in self.unused_params):
+            if merged and merged[-1][1] == a:
+                merged[-1][1] = b
+            else:
+                merged.append([a, b])
+        if len(merged) > 256:
+            raise RuntimeError("more than 256 never-trained parameter spans")
+        self.skip_spans = torch.tensor(merged, dtype=torch.int64, device=dev).reshape(-1) if merged else None
+        self.n_skip = len(merged)
         self.jt = torch.empty(self.B, J, 3, dtype=torch.float32, device=dev)
         ns = len(self.sup_heads)
         self.uvd_all = [torch.empty(self.B, J, 3, dtype=torch.float32, device=dev) for _ in range(ns)]
@@ -57,7 +82,7 @@ class FusedTrainer:
         self.loss_host = torch.zeros(ns, 2, dtype=torch.float32).pin_memory()
         self.steps_done = 0
         self.use_graph = use_graph
-        self.graph_fb = self.graph_opt = None
+        self.graph_fb = self.graph_opt = self.graph_step = None
         self._pipe = None
         self.side = torch.cuda.Stream(device=dev)          # weight-gradient GEMMs overlap the dgrad / BatchNorm backward chain
         if self.plan.precision == "bf16":
@@ -72,11 +97,13 @@ class FusedTrainer:
         if part == 1:
             pl.run_backward(s, side=self.side, part=1)
             return
-        pl.arena_used().zero_()
-        st.grads.zero_()
+        au = pl.arena_used()
+        L.check(self.lib.awr_memset_zero(au.data_ptr(), au.numel() * 4, s), "awr_memset_zero")        # BN accumulators: a memset node, no fill kernel
+        if self.keep_grads:                      # otherwise the optimizer kernel of the previous step left the buffer zeroed
+            L.check(self.lib.awr_memset_zero(st.grads.data_ptr(), st.grads.numel() * 4, s), "awr_memset_zero")
         for h in pl.heads:
             if h not in self.sup_heads:
-                h.dpred.zero_()
+                L.check(self.lib.awr_memset_zero(h.dpred.data_ptr(), h.dpred.numel() * 4, s), "awr_memset_zero")
         pl.run_forward(s)
         for i, hd in enumerate(self.sup_heads):
             uvd, ws, loss = self.uvd_all[i], self.ws_all[i], self.loss_all[i]
@@ -91,17 +118,24 @@ class FusedTrainer:
         st, s = self.store, L.stream()
         L.check(self.lib.awr_adam_tick(self.step_dev.data_ptr(), s), "awr_adam_tick")
         shadow = st.shadow.data_ptr() if self.plan.precision == "bf16" else None
-        L.check(self.lib.awr_adam_flat(st.params.data_ptr(), st.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), shadow,
-                                       st.params.numel(), self.step_dev.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                       self.wd, 1.0 / self.world, s), "awr_adam_flat")
+        skip = self.skip_spans.data_ptr() if self.n_skip else None
+        zero = 0 if self.keep_grads else 1
+        if self.optimizer == "adam":
+            L.check(self.lib.awr_optim_adam(st.params.data_ptr(), st.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), shadow,
+                                            st.params.numel(), self.hyper.data_ptr(), self.betas[0], self.betas[1], self.eps, self.wd,
+                                            1.0 / self.world, skip, self.n_skip, zero, s), "awr_optim_adam")
+        else:
+            L.check(self.lib.awr_optim_sgd(st.params.data_ptr(), st.grads.data_ptr(), self.m.data_ptr(), shadow, st.params.numel(),
+                                           self.hyper.data_ptr(), self.momentum, self.wd, 1.0 / self.world, skip, self.n_skip, zero, s),
+                    "awr_optim_sgd")
 
     def _allreduce(self):
         if self.world > 1:
             dp.allreduce_sum_(self.store.grads, self.pg)        # NCCL over NVLink; 1/world is applied inside awr_adam_flat
 
     def _overlapped(self):
-        """Data-parallel step with the all-reduce of the early gradient bucket (last layers: most of the bytes) overlapping the rest of
-        backward: graph A -> async NCCL on bucket 1 -> graph B -> async NCCL on bucket 0 -> wait both -> Adam graph."""
+        """Fallback data-parallel step (AWR_B200_DP_GRAPH=0): graph A -> async NCCL on bucket 1 -> graph B -> async NCCL on bucket 0 ->
+        wait both -> optimizer graph, all driven from the host."""
         import torch.distributed as dist
         off = self.plan.bwd_split[1]
         g = self.store.grads
@@ -112,14 +146,61 @@ class FusedTrainer:
         w1.wait(); w0.wait()
         self.graph_opt.replay()
 
+    def _dp_step_body(self):
+        """The whole data-parallel step as ONE capturable sequence: forward, head, backward up to the gradient-bucket split; the all-reduce
+        of the early bucket (last layers: ~80 % of the bytes) on a communication stream WHILE the rest of backward runs with `nccl_sms`
+        SMs left free for it (the persistent conv kernels otherwise occupy all 148 and the collective queues behind them: round 1
+        measured 96 % of the all-reduce exposed); the small late bucket; the optimizer.  NCCL calls are captured into the CUDA graph,
+        so a step is one graph replay with no host-side collective enqueue."""
+        import torch.distributed as dist
+        main = torch.cuda.current_stream()
+        g = self.store.grads
+        if self.plan.bwd_split is None:
+            self._fwd_bwd()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+        else:
+            off = self.plan.bwd_split[1]
+            self._fwd_bwd(part=0)
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(g[off:], op=dist.ReduceOp.SUM, group=self.pg)
+            prev = self.lib.awr_set_sm_budget(148 - self.nccl_sms)
+            try:
+                self._fwd_bwd(part=1)
+            finally:
+                self.lib.awr_set_sm_budget(prev)
+            dist.all_reduce(g[:off], op=dist.ReduceOp.SUM, group=self.pg)
+            main.wait_stream(self.comm)
+        self._opt()
+
     def _capture(self):
+        # warm-up outside capture (lazy module loads, first-touch).  It is a real forward/backward on the batch in the static buffers:
+        # the BatchNorm running statistics / num_batches_tracked it advanced are put back, and its gradients are discarded, so the first
+        # replayed step starts from exactly the state the reference would be in.
+        saved = {k: b.clone() for k, b in self.store.buffers.items()}
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):           # warm-up outside capture (lazy module loads, first-touch)
+        with torch.cuda.stream(side):
             self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        for k, b in self.store.buffers.items():
+            b.copy_(saved[k])
+        self.store.grads.zero_()
         self.split = self.world > 1 and self.plan.bwd_split is not None and os.environ.get("AWR_B200_NO_OVERLAP") != "1"
+        self.graph_step = None
+        if self.world > 1 and os.environ.get("AWR_B200_DP_GRAPH", "1") == "1":
+            import torch.distributed as dist
+            warm = torch.zeros(8, device=self.device)
+            dist.all_reduce(warm, group=self.pg)                 # communicator / channels exist before capture
+            torch.cuda.synchronize()
+            self.comm = torch.cuda.Stream(device=self.device)
+            self.nccl_sms = int(os.environ.get("AWR_B200_NCCL_SMS", "16"))
+            self.graph_step = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_step):
+                self._dp_step_body()
+            self.graph_fb = self.graph_step
+            return
         self.graph_fb = torch.cuda.CUDAGraph()
         self.graph_fb2 = None
         if self.split:
@@ -134,7 +215,6 @@ class FusedTrainer:
         self.graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_opt):
             self._opt()
-        # the warm-up / capture passes advanced BN running statistics but not the parameters or the Adam state
 
     # ---- public API -------------------------------------------------------------------------------------
     def load_batch(self, img, jt_uvd_gt):
@@ -144,16 +224,23 @@ class FusedTrainer:
 
     def run_step(self):
         """One optimisation step on the batch currently in the static buffers; no host sync."""
+        if self.plan.precision == "bf16" and getattr(self.module, "_params_dirty", False):
+            self.store.refresh_shadow()          # load_state_dict() after construction: the bf16 weight shadow follows the new parameters
+            self.module._params_dirty = False
         if self.use_graph:
             if self.graph_fb is None:
                 self._capture()
-            if self.split:
+            if self.graph_step is not None:
+                self.graph_step.replay()
+            elif self.split:
                 self._overlapped()
             else:
                 self.graph_fb.replay()
                 self._allreduce()
                 self.graph_opt.replay()
         else:
+            if not self.keep_grads and self.steps_done == 0:
+                self.store.grads.zero_()
             self._fwd_bwd()
             self._allreduce()
             self._opt()
@@ -233,41 +320,104 @@ class FusedTrainer:
                 self.store.refresh_shadow()
 
     def set_lr(self, lr):
-        """Learning-rate schedules (train.py:68-69 StepLR / ReduceLROnPlateau drive `optimizer.param_groups[0]['lr']`): the rate is a
-        launch argument of the captured Adam graph, so a change re-captures that two-kernel graph; the forward/backward graph is untouched."""
-        lr = float(lr)
-        if lr == self.lr:
-            return
-        self.lr = lr
-        if self.graph_opt is not None:
-            self.graph_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_opt):
-                self._opt()
+        """Learning-rate schedules (train.py:89-96,157-160: StepLR / ReduceLROnPlateau drive `optimizer.param_groups[0]['lr']`): the rate is
+        a device scalar the optimizer kernel reads, so the captured graphs are untouched (awr_b200.optim wraps this)."""
+        self.lr = float(lr)
+        self.hyper[1:2].fill_(self.lr)
+
+    @property
+    def param_groups(self):
+        """torch.optim-style view for schedulers and logging (train.py:155 prints optimizer.param_groups[0]['lr'])."""
+        return [_LRGroup(self)]
 
     def load_optimizer_state_dict(self, sd):
-        """Inverse of optimizer_state_dict(): resume from the `optimizer` entry of a checkpoint (train.py:89-96), i.e. a torch.optim.Adam
-        state over the canonical parameter order.  Parameters the reference never steps (unused Hourglass skip layers) may be absent."""
+        """Inverse of optimizer_state_dict(): resume from the `optimizer` entry of a checkpoint (train.py:82-84), i.e. a torch.optim
+        Adam / SGD state over the canonical parameter order.  State keys are whatever `param_groups[0]['params']` lists -- positions in
+        current torch, `id(param)` values in the torch<=1.1 checkpoints the reference ships (results/hourglass_1.pth: 220 entries for
+        250 parameters: the never-trained ones are absent)."""
         lay = self.store.layout
-        self.m.zero_(); self.v.zero_()
+        self.m.zero_()
+        if self.v is not None:
+            self.v.zero_()
+        keys = list(sd["param_groups"][0]["params"])
+        if len(keys) != len(self.module._pnames):
+            raise ValueError(f"optimizer state has {len(keys)} parameters, the module has {len(self.module._pnames)}")
         steps = 0
-        for i, name in enumerate(self.module._pnames):
-            st = sd["state"].get(i)
+        for key, name in zip(keys, self.module._pnames):
+            st = sd["state"].get(key)
             if st is None:
                 continue
-            lay.view(self.m, name).copy_(st["exp_avg"].to(self.device))
-            lay.view(self.v, name).copy_(st["exp_avg_sq"].to(self.device))
-            steps = max(steps, int(float(st["step"])))
-        self.steps_done = steps
-        self.step_dev.fill_(float(steps))
+            if self.optimizer == "adam":
+                lay.view(self.m, name).copy_(st["exp_avg"].to(self.device))
+                lay.view(self.v, name).copy_(st["exp_avg_sq"].to(self.device))
+                steps = max(steps, int(float(st["step"])))
+            elif st.get("momentum_buffer") is not None:
+                lay.view(self.m, name).copy_(st["momentum_buffer"].to(self.device))
+        if self.optimizer == "adam":
+            self.steps_done = steps
+            self.hyper[0:1].fill_(float(steps))
         self.set_lr(sd["param_groups"][0]["lr"])
 
     def optimizer_state_dict(self):
-        """torch.optim.Adam-shaped state (train.py:165-172 saves optimizer.state_dict()) over the canonical parameters."""
-        lay, st = self.store.layout, self.store
+        """torch.optim-shaped state (train.py:165-172 saves optimizer.state_dict()) over the canonical parameters; like torch, parameters
+        that never received a gradient have no state entry."""
+        lay = self.store.layout
         state = {}
+        unused = set(self.unused_params)
         for i, name in enumerate(self.module._pnames):
-            state[i] = {"step": torch.tensor(float(self.steps_done)), "exp_avg": lay.view(self.m, name).clone(),
-                        "exp_avg_sq": lay.view(self.v, name).clone()}
-        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
-                 "params": list(range(len(self.module._pnames)))}
+            if name in unused or self.steps_done == 0:
+                continue
+            if self.optimizer == "adam":
+                state[i] = {"step": torch.tensor(float(self.steps_done)), "exp_avg": lay.view(self.m, name).clone(),
+                            "exp_avg_sq": lay.view(self.v, name).clone()}
+            else:
+                state[i] = {"momentum_buffer": lay.view(self.m, name).clone()}
+        if self.optimizer == "adam":
+            group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False}
+        else:
+            group = {"lr": self.lr, "momentum": self.momentum, "dampening": 0, "weight_decay": self.wd, "nesterov": False}
+        group["params"] = list(range(len(self.module._pnames)))
         return {"state": state, "param_groups": [group]}
+
+    # ---- checkpoints in the reference's layout (train.py:165-172 / :80-86; test.py:45-49) -------------------------------------------
+    def save_checkpoint(self, path, best_records=None, rank=0):
+        """{'model', 'optimizer', 'best_records'} exactly as train.py:165-172 writes it: `module.`-free keys, fp32 CPU tensors.  Under data
+        parallelism only `rank` 0 writes (every replica holds the same parameters; BatchNorm running statistics are rank 0's, DDP-style)."""
+        if rank != 0:
+            return False
+        sd = {k: v.detach().cpu().clone() for k, v in self.module.state_dict().items()}
+        osd = self.optimizer_state_dict()
+        for st in osd["state"].values():
+            for k, v in list(st.items()):
+                if torch.is_tensor(v):
+                    st[k] = v.cpu()
+        torch.save({"model": sd, "optimizer": osd, "best_records": dict(best_records or {"epoch": 0, "MPE": 1e10, "AUC": 0})}, path)
+        return True
+
+    def load_checkpoint(self, path_or_dict, load_optimizer=True):
+        """train.py:80-86: model + optimizer (+ best_records, returned).  Accepts the reference's legacy pickles (numpy scalars in
+        best_records), hence weights_only=False: only load checkpoints you trust."""
+        ck = torch.load(path_or_dict, map_location="cpu", weights_only=False) if isinstance(path_or_dict, (str, bytes, os.PathLike)) else path_or_dict
+        self.module.load_state_dict(ck["model"], strict=True)
+        if self.plan.precision == "bf16":
+            self.store.refresh_shadow()
+            self.module._params_dirty = False
+        if load_optimizer and "optimizer" in ck:
+            self.load_optimizer_state_dict(ck["optimizer"])
+        return ck.get("best_records")
+
+
+class _LRGroup(dict):
+    """param_groups[0] of a FusedTrainer: reading/writing ['lr'] reads/sets the device-side learning rate."""
+
+    def __init__(self, trainer):
+        super().__init__(lr=trainer.lr)
+        self._tr = trainer
+
+    def __getitem__(self, k):
+        return self._tr.lr if k == "lr" else super().__getitem__(k)
+
+    def __setitem__(self, k, v):
+        if k == "lr":
+            self._tr.set_lr(v)
+        super().__setitem__(k, v)

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--layers", default="", help="write a per-layer conv timing table to gpurun_out/<name>")
     ap.add_argument("--gpu-eager-baseline", action="store_true",
                     help="also time the oracle's torch ops on this GPU (eager cuDNN/cuBLAS, fp32 and bf16 autocast): a reported bar, never the product")
+    ap.add_argument("--keep-grads", action="store_true", help="A/B: separate gradient fill per step instead of zeroing in the optimizer kernel")
     ap.add_argument("--no-parity", action="store_true", help="skip the C1 parity leg (UVD max-abs-diff vs the reference golden vector)")
     return ap.parse_args()
 
@@ -337,7 +338,7 @@ def main():
     kind, n = a.net.split("_")
     net = awr_b200.get_deconv_net(int(n), J, ds, precision=a.precision) if kind == "resnet" else awr_b200.PoseNet(a.net, J, precision=a.precision)
     net = net.to(dev)
-    tr = FusedTrainer(net, a.batch, H, ks, 1.0, 1.0, lr=1e-3, world_size=world, use_graph=not a.no_graph)
+    tr = FusedTrainer(net, a.batch, H, ks, 1.0, 1.0, lr=1e-3, world_size=world, use_graph=not a.no_graph, keep_grads=a.keep_grads)
     tr.broadcast_parameters(0)
 
     # synthetic batch, per-rank seed; a few distinct batches rotate through the e2e leg

@@ -191,8 +191,17 @@ int awr_optim_adam(float* p, float* g, float* m, float* v, void* bf16_shadow, lo
                    void* stream);
 int awr_optim_sgd(float* p, float* g, float* momentum_buf, void* bf16_shadow, long long n, const float* hyper_dev, float momentum,
                   float weight_decay, float grad_scale, const long long* skip_spans_dev, int n_skip, int zero_grad, void* stream);
+/* Deterministic build (awr_deterministic() == 1, libawr_b200_det.so): the weight-gradient kernels (awr_conv_wgrad_tc / _simt,
+ * awr_stem_wgrad) take dW / dbias as awr_acc_t slots instead of floats -- same element offsets -- so split-K partial sums combine
+ * order-independently; this folds n slots into the fp32 gradients (grads[i] += value) and re-zeroes them.  In the default build the
+ * kernels add fp32 atomics straight into the float gradient buffer and this call is not needed. */
+int awr_deterministic(void);
+int awr_grad_acc_finalize(void* acc, float* grads, long long n, void* stream);
 /* cudaMemsetAsync(p, 0, nbytes) on `stream` (a memset node when captured): the per-step zero fill of the accumulator arena. */
 int awr_memset_zero(void* p, long long nbytes, void* stream);
+/* Grid cap (SMs) of the persistent tensor-core kernels launched from now on, 8..148; returns the previous value.  The data-parallel
+ * trainer lowers it for the launches that overlap a gradient bucket's NCCL all-reduce, so the collective finds free SMs. */
+int awr_set_sm_budget(int n);
 int awr_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 
 /* ---- convolutions, CUDA-core fp32-accumulate path (fp32 precision mode; also the 1-channel stem) --------------
@@ -212,7 +221,7 @@ int awr_conv_simt(const void* in, const float* w, const float* bias, void* out, 
 /* Weight gradient  dW[tap*w_tap + i*s_p + j*s_g] += sum_q pointwise[q,i] * gathered[q*stride - pad + tap, j]
  * (q over the coarse grid N x Hc x Wc).  Conv2d: pointwise=dy, gathered=x, s_p=Cin, s_g=1.
  * ConvTranspose2d: pointwise=x, gathered=dy, s_p=1, s_g=Cin.  dW fp32, caller zero-fills. */
-int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, int dtype, int N, int Hc, int Wc, int Cp, int Hf, int Wf,
+int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, void* dW, int dtype, int N, int Hc, int Wc, int Cp, int Hf, int Wf,
                         int Cg, int R, int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
 
 /* 1-channel k x k stride-1 'same' stem convolution: x (N,H,W) fp32, w [k*k][Cout] fp32, bias or NULL -> y NHWC.
@@ -220,7 +229,7 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, float* dW, 
 int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, void* stats, int dtype, int N, int H, int W, int Cout, int k,
                   void* stream);
 /* dW[k*k][Cout] += ..., dbias[Cout] += ... (dbias may be NULL); caller zero-fills. */
-int awr_stem_wgrad(const float* x, const void* dy, float* dW, float* dbias, int dtype, int N, int H, int W, int Cout, int k,
+int awr_stem_wgrad(const float* x, const void* dy, void* dW, void* dbias, int dtype, int N, int H, int W, int Cout, int k,
                    void* stream);
 
 /* ---- convolutions, tcgen05 tensor-core path (bf16 precision mode) ------------------------------------------------
@@ -236,7 +245,7 @@ int awr_conv_tc(const void* in, const void* w, const float* bias, void* out, voi
 
 /* Weight gradient on tensor cores; same argument meaning as awr_conv_wgrad_simt (bf16 NHWC operands, fp32 dW accumulated with
  * atomic adds: caller zero-fills).  The contraction runs over pixels; both operands are MN-major TMA boxes of the NHWC tensors. */
-int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, float* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
+int awr_conv_wgrad_tc(const void* pointwise, const void* gathered, void* dW, int N, int Hc, int Wc, int Cp, int Hf, int Wf, int Cg, int R,
                       int S, int stride, int pad, int s_p, int s_g, int w_tap, void* stream);
 
 #ifdef __cplusplus

@@ -29,10 +29,16 @@ def _conv_tc(x, w_phys, bias, out, N, Hi, Wi, Ck, Ho, Wo, Cn, k, stride, pad, tr
 
 
 def _wgrad_tc(pw, ga, dW, N, Hc, Wc, Cp, Hf, Wf, Cg, k, stride, pad, s_p, s_g, w_tap):
+    """dW: fp32 (zero-filled).  In the bit-reproducible build the kernel accumulates into awr_acc_t slots that awr_grad_acc_finalize folds
+    into the fp32 array -- the same two calls engine.Plan makes."""
     from awr_b200 import _lib as L
-    L.check(L.lib().awr_conv_wgrad_tc(pw.data_ptr(), ga.data_ptr(), dW.data_ptr(), N, Hc, Wc, Cp, Hf, Wf, Cg, k, k, stride, pad, s_p, s_g, w_tap,
+    tgt = L.acc_zeros(dW.numel(), dW.device) if L.deterministic() else dW
+    L.check(L.lib().awr_conv_wgrad_tc(pw.data_ptr(), ga.data_ptr(), tgt.data_ptr(), N, Hc, Wc, Cp, Hf, Wf, Cg, k, k, stride, pad, s_p, s_g, w_tap,
                                       L.stream()), "awr_conv_wgrad_tc")
-    torch.cuda.synchronize()
+    if L.deterministic():
+        L.check(L.lib().awr_grad_acc_finalize(tgt.data_ptr(), dW.data_ptr(), dW.numel(), L.stream()), "awr_grad_acc_finalize")
+        torch.cuda.synchronize()
+        assert int(tgt.abs().sum()) == 0            # slots are re-armed for the next step
 
 
 CONV_CASES = [  # N, Cin, Cout, H, k, stride, pad

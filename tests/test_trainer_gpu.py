@@ -45,12 +45,13 @@ def test_fused_step_fp32_vs_oracle(net, ks):
     img, jt = O.synthetic_batch(B, H, J, 23)
     loss, lc, ld, uvd, pred, grads, new_stats = O.loss_and_grads(sd, img, jt, net, ds, ks, 0.7, 1.3)
 
-    tr = FusedTrainer(m, B, H, ks, 0.7, 1.3, lr=1e-3, use_graph=True)
-    # graph capture runs warm-up passes that advance BN running stats: reload them so the compared step starts from `sd`
+    tr = FusedTrainer(m, B, H, ks, 0.7, 1.3, lr=1e-3, use_graph=True, keep_grads=True)
+    # graph capture runs a warm-up pass; it must leave the module exactly as it was (BN running statistics, num_batches_tracked)
     before = {k: v.clone() for k, v in m.state_dict().items()}
     tr.load_batch(img.cuda(), jt.cuda())
     tr._capture()
-    m.load_state_dict(before, strict=True)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), f"capture warm-up changed {k}"
     l0, l1 = tr.train_step(img.cuda(), jt.cuda())
     assert abs(l0 - lc.item()) < 2e-3 * abs(lc.item()) + 1e-9
     assert abs(l1 - ld.item()) < 2e-3 * abs(ld.item()) + 1e-9
@@ -80,7 +81,12 @@ def test_fused_step_fp32_vs_oracle(net, ks):
             assert torch.allclose(st[k].cpu(), v, rtol=1e-3, atol=1e-5), k
     assert tr.step_dev.item() == 1.0
     od = tr.optimizer_state_dict()
-    assert len(od["state"]) == len(list(m.parameters())) and od["param_groups"][0]["lr"] == 1e-3
+    # like torch.optim, parameters whose gradient is None (unused Hourglass skip_layer convs) carry no state: 220 of 250 for hourglass_1,
+    # as in the reference's shipped results/hourglass_1.pth
+    n_unused = sum(1 for g in grads.values() if g is None)
+    assert len(tr.unused_params) == n_unused == (0 if kind == "resnet" else 30)
+    assert len(od["state"]) == len(list(m.parameters())) - n_unused and od["param_groups"][0]["lr"] == 1e-3
+    assert int(st["pre.1.num_batches_tracked" if kind == "resnet" else "pre.0.bn.num_batches_tracked"]) == int(sd["pre.1.num_batches_tracked" if kind == "resnet" else "pre.0.bn.num_batches_tracked"]) + 1
 
 
 def test_lagged_pipeline_matches_blocking_steps():
@@ -137,7 +143,7 @@ def test_all_stacks_supervision_vs_oracle():
     loss, lc, ld, uvd, pred, grads, _ = O.loss_and_grads(sd, img, jt, net, ds, ks, 0.7, 1.3, all_stacks=True)
     last = O.loss_and_grads(sd, img, jt, net, ds, ks, 0.7, 1.3)
     assert lc.item() > 1.5 * last[1].item()                                  # two stacks really contribute
-    tr = FusedTrainer(m, B, H, ks, 0.7, 1.3, lr=1e-3, use_graph=False, all_stacks=True)
+    tr = FusedTrainer(m, B, H, ks, 0.7, 1.3, lr=1e-3, use_graph=False, all_stacks=True, keep_grads=True)
     assert len(tr.sup_heads) == 2
     l0, l1 = tr.train_step(img.cuda(), jt.cuda())
     assert abs(l0 - lc.item()) < 2e-3 * abs(lc.item()) and abs(l1 - ld.item()) < 2e-3 * abs(ld.item())
@@ -168,7 +174,7 @@ def test_set_lr_and_optimizer_state_roundtrip():
     tr = FusedTrainer(m, B, H, 1.0, 1.0, 1.0, lr=1e-3, use_graph=True)
     tr.train_step(img, jt)
     p1 = tr.store.params.clone()
-    tr.set_lr(0.0)                                                            # re-captures the Adam graph only
+    tr.set_lr(0.0)                                                            # a 4-byte device write: the captured graphs are untouched
     tr.train_step(img, jt)
     assert torch.equal(tr.store.params, p1) and tr.step_dev.item() == 2.0    # zero rate: moments advance, parameters do not
     tr.set_lr(1e-4)

@@ -251,7 +251,8 @@ class Plan:
             self._build_hourglass(int(n))
         else:
             raise ValueError(net)
-        self.bwd_split = None          # (launch index, flat gradient offset): gradients at/after the offset are final after that many launches
+        self.bwd_split = None          # first entry of bwd_splits (kept for callers that use a single early bucket)
+        self.bwd_splits = []           # [(launch index, flat gradient offset)]: gradients at/after the offset are final after that many launches
         if training:
             marks = {}
             for i in range(len(self.ops) - 1, -1, -1):
@@ -300,7 +301,8 @@ class Plan:
                 return off, off + int(math.prod(shp))
             sp = lay.specs[name]
             return sp.offset, sp.offset + sp.numel
-        total, best = lay.total, None
+        total = lay.total
+        cands = []                     # (launch count, offset, fraction of the buffer that is final), in backward order
         lo = total
         for i in range(len(self.ops) - 1, 0, -1):
             for n in self._op_param_names(self.ops[i]):
@@ -315,13 +317,26 @@ class Plan:
                 if not ok:
                     break
             frac = (total - lo) / total
-            if ok and frac >= 0.5:
-                if best is None or abs(frac - 0.8) < abs(best[2] - 0.8):
-                    best = (marks[i], lo, frac)
-            if frac > 0.95:
+            if ok and 0 < marks[i] < len(self.bwd) and frac >= 0.5:
+                cands.append((marks[i], lo, frac))
+        # gradient buckets for the data-parallel all-reduce: the first closes when ~80 % of the bytes are final (its all-reduce overlaps
+        # the rest of backward), then ~95 % and ~99 %, so that what is reduced AFTER backward is a fraction of a megabyte
+        picked = []
+        for target in (0.80, 0.95, 0.99):
+            pool = [c for c in cands if not picked or (c[0] > picked[-1][0] and c[1] < picked[-1][1])]
+            if not pool:
                 break
-        if best is not None and 0 < best[0] < len(self.bwd):
-            self.bwd_split = (best[0], best[1])
+            best = min(pool, key=lambda c: abs(c[2] - target))
+            if picked and best[2] - picked[-1][2] < 0.02:
+                continue
+            picked.append(best)
+        self.bwd_splits = [(c[0], c[1]) for c in picked]
+        self.bwd_split = self.bwd_splits[0] if self.bwd_splits else None
+
+    def bucket_range(self, part):
+        """[a, b) of the flat gradient buffer that is final once backward part `part` has run."""
+        offs = [self.store.grads.numel()] + [c[1] for c in self.bwd_splits] + [0]
+        return offs[part + 1], offs[part]
 
     # ---- infrastructure ---------------------------------------------------------------------------
     def arena(self, n):
@@ -385,8 +400,9 @@ class Plan:
         under CUDA-graph capture (the fork/join events become graph edges)."""
         s = L.stream() if stream is None else stream
         lo, hi = 0, len(self.bwd)
-        if part is not None and self.bwd_split is not None:        # part 0: launches before the split, part 1: the rest
-            lo, hi = (0, self.bwd_split[0]) if part == 0 else (self.bwd_split[0], len(self.bwd))
+        if part is not None and self.bwd_splits:                   # part i: launches between split i-1 and split i (0 .. len(splits))
+            cuts = [0] + [c[0] for c in self.bwd_splits] + [len(self.bwd)]
+            lo, hi = cuts[part], cuts[part + 1]
         if side is None:
             for f in self.bwd[lo:hi]:
                 f(s)
@@ -404,8 +420,8 @@ class Plan:
             # bit-reproducible build: fold the accumulator slots of the gradients that are final now into the fp32 buffer
             n = self.store.grads.numel()
             a, b = 0, n
-            if part is not None and self.bwd_split is not None:
-                a, b = (self.bwd_split[1], n) if part == 0 else (0, self.bwd_split[1])
+            if part is not None and self.bwd_splits:
+                a, b = self.bucket_range(part)
             L.check(self.lib.awr_grad_acc_finalize(acc.data_ptr() + 16 * a, self.store.grads.data_ptr() + 4 * a, b - a, s), "awr_grad_acc_finalize")
 
     # ---- ops ------------------------------------------------------------------------------------------

@@ -92,10 +92,11 @@ class FusedTrainer:
 
     # ---- launch sequences -------------------------------------------------------------------------------
     def _fwd_bwd(self, part=None):
-        """part None: whole forward+backward; 0: forward + head + backward up to the gradient-bucket split; 1: rest of backward."""
+        """part None: whole forward+backward; 0: forward + head + backward up to the first gradient-bucket split; i > 0: backward
+        between splits i-1 and i (engine.Plan.bwd_splits)."""
         pl, st, s = self.plan, self.store, L.stream()
-        if part == 1:
-            pl.run_backward(s, side=self.side, part=1)
+        if part is not None and part > 0:
+            pl.run_backward(s, side=self.side, part=part)
             return
         au = pl.arena_used()
         L.check(self.lib.awr_memset_zero(au.data_ptr(), au.numel() * 4, s), "awr_memset_zero")        # BN accumulators: a memset node, no fill kernel
@@ -137,13 +138,14 @@ class FusedTrainer:
         """Fallback data-parallel step (AWR_B200_DP_GRAPH=0): graph A -> async NCCL on bucket 1 -> graph B -> async NCCL on bucket 0 ->
         wait both -> optimizer graph, all driven from the host."""
         import torch.distributed as dist
-        off = self.plan.bwd_split[1]
-        g = self.store.grads
-        self.graph_fb.replay()
-        w1 = dist.all_reduce(g[off:], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        self.graph_fb2.replay()
-        w0 = dist.all_reduce(g[:off], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-        w1.wait(); w0.wait()
+        g, pl = self.store.grads, self.plan
+        works = []
+        for part, gr in enumerate(self.graph_parts):
+            gr.replay()
+            a, b = pl.bucket_range(part)
+            works.append(dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
         self.graph_opt.replay()
 
     def _dp_step_body(self):
@@ -155,21 +157,25 @@ class FusedTrainer:
         import torch.distributed as dist
         main = torch.cuda.current_stream()
         g = self.store.grads
-        if self.plan.bwd_split is None:
+        pl = self.plan
+        if not pl.bwd_splits:
             self._fwd_bwd()
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
         else:
-            off = self.plan.bwd_split[1]
-            self._fwd_bwd(part=0)
-            self.comm.wait_stream(main)
-            with torch.cuda.stream(self.comm):
-                dist.all_reduce(g[off:], op=dist.ReduceOp.SUM, group=self.pg)
-            prev = self.lib.awr_set_sm_budget(148 - self.nccl_sms)
-            try:
-                self._fwd_bwd(part=1)
-            finally:
-                self.lib.awr_set_sm_budget(prev)
-            dist.all_reduce(g[:off], op=dist.ReduceOp.SUM, group=self.pg)
+            nparts = len(pl.bwd_splits) + 1
+            prev = None
+            for part in range(nparts):
+                self._fwd_bwd(part=part)
+                a, b = pl.bucket_range(part)
+                if part == 0:                                 # from here on a collective is in flight: leave it its SMs
+                    prev = self.lib.awr_set_sm_budget(max(8, 148 - self.nccl_sms))
+                if part < nparts - 1:
+                    self.comm.wait_stream(main)
+                    with torch.cuda.stream(self.comm):
+                        dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg)
+                else:
+                    self.lib.awr_set_sm_budget(prev)
+                    dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg)      # the last, sub-megabyte bucket: nothing left to hide it behind
             main.wait_stream(self.comm)
         self._opt()
 
@@ -187,7 +193,7 @@ class FusedTrainer:
         for k, b in self.store.buffers.items():
             b.copy_(saved[k])
         self.store.grads.zero_()
-        self.split = self.world > 1 and self.plan.bwd_split is not None and os.environ.get("AWR_B200_NO_OVERLAP") != "1"
+        self.split = self.world > 1 and bool(self.plan.bwd_splits) and os.environ.get("AWR_B200_NO_OVERLAP") != "1"
         self.graph_step = None
         if self.world > 1 and os.environ.get("AWR_B200_DP_GRAPH", "1") == "1":
             import torch.distributed as dist
@@ -195,7 +201,8 @@ class FusedTrainer:
             dist.all_reduce(warm, group=self.pg)                 # communicator / channels exist before capture
             torch.cuda.synchronize()
             self.comm = torch.cuda.Stream(device=self.device)
-            self.nccl_sms = int(os.environ.get("AWR_B200_NCCL_SMS", "16"))
+            # SMs kept free of persistent conv CTAs while a bucket is in flight (AWR_B200_SM_RESERVE; default = NCCL's CTA cap)
+            self.nccl_sms = int(os.environ.get("AWR_B200_SM_RESERVE", os.environ.get("AWR_B200_NCCL_SMS", "16")))
             self.graph_step = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_step):
                 self._dp_step_body()
@@ -204,11 +211,12 @@ class FusedTrainer:
         self.graph_fb = torch.cuda.CUDAGraph()
         self.graph_fb2 = None
         if self.split:
-            with torch.cuda.graph(self.graph_fb):
-                self._fwd_bwd(part=0)
-            self.graph_fb2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_fb2):
-                self._fwd_bwd(part=1)
+            self.graph_parts = []
+            for part in range(len(self.plan.bwd_splits) + 1):
+                gr = self.graph_fb if part == 0 else torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._fwd_bwd(part=part)
+                self.graph_parts.append(gr)
         else:
             with torch.cuda.graph(self.graph_fb):
                 self._fwd_bwd()
@@ -318,6 +326,12 @@ class FusedTrainer:
             dp.broadcast_([self.store.params] + list(self.store.buffers.values()), src, self.pg)
             if self.plan.precision == "bf16":
                 self.store.refresh_shadow()
+
+    def release(self):
+        """Drop the captured graphs (they hold the NCCL communicator busy: do this before tearing the process group down)."""
+        torch.cuda.synchronize()
+        self.graph_fb = self.graph_opt = self.graph_step = None
+        self.graph_parts = []
 
     def set_lr(self, lr):
         """Learning-rate schedules (train.py:89-96,157-160: StepLR / ReduceLROnPlateau drive `optimizer.param_groups[0]['lr']`): the rate is

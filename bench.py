@@ -412,8 +412,11 @@ def main():
             scratch = torch.zeros_like(tr.store.grads)
             ar_ms, ar_bw = dp.allreduce_busbw(scratch, reps=10)
             allreduce = {"bytes": scratch.numel() * 4, "ms": round(ar_ms, 4), "busbw_gbs": round(ar_bw, 1), "nvlink_peak_gbs_per_direction": 900,
-                         "how": "10 NCCL sum all-reduces of a gradient-sized fp32 buffer alone, CUDA events, max over ranks; "
-                                "in the step 82 % of these bytes overlap the rest of backward"}
+                         "how": "10 NCCL sum all-reduces of a gradient-sized fp32 buffer alone, CUDA events, max over ranks; in the step the buffer "
+                                "goes in buckets as backward finalises it (captured in the step's CUDA graph), all but the last, "
+                                "sub-megabyte bucket overlapping the rest of backward",
+                         "buckets_bytes": [4 * (b - a_) for a_, b in (tr.plan.bucket_range(i) for i in range(len(tr.plan.bwd_splits) + 1))],
+                         "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
             del scratch
         except Exception as e:              # never lose the bench line to a reporting leg
             allreduce = {"error": f"{type(e).__name__}: {e}"[:200]}
@@ -492,7 +495,12 @@ def main():
             line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured step graph holds NCCL kernels: release it, then leave without the communicator teardown (destroy_process_group can
+        # block on a communicator that graph-captured collectives used); every rank exits 0 after the line is out
+        sys.stdout.flush()
+        dist.barrier()
+        tr.release()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -24,6 +24,16 @@ from . import dp
 from .modules import AWRBackbone
 
 
+def map_optimizer_state(sd, pnames):
+    """torch.optim state_dict -> {canonical parameter name: per-parameter state}.  State keys are whatever `param_groups[*]['params']`
+    lists, in parameter order: positions in current torch, `id(param)` values in the torch<=1.1 pickles the reference ships
+    (results/hourglass_1.pth: 250 parameters, 220 state entries -- the skip_layer convs forward never calls have none)."""
+    keys = [k for g in sd["param_groups"] for k in g["params"]]
+    if len(keys) != len(pnames):
+        raise ValueError(f"optimizer state lists {len(keys)} parameters, the module has {len(pnames)}")
+    return {name: sd["state"][key] for key, name in zip(keys, pnames) if key in sd["state"]}
+
+
 class FusedTrainer:
     def __init__(self, module: AWRBackbone, batch_size, img_size, kernel_size, coord_weight=1.0, dense_weight=1.0, lr=1e-3,
                  betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1, use_graph=True, process_group=None, all_stacks=False,
@@ -353,14 +363,8 @@ class FusedTrainer:
         self.m.zero_()
         if self.v is not None:
             self.v.zero_()
-        keys = list(sd["param_groups"][0]["params"])
-        if len(keys) != len(self.module._pnames):
-            raise ValueError(f"optimizer state has {len(keys)} parameters, the module has {len(self.module._pnames)}")
         steps = 0
-        for key, name in zip(keys, self.module._pnames):
-            st = sd["state"].get(key)
-            if st is None:
-                continue
+        for name, st in map_optimizer_state(sd, self.module._pnames).items():
             if self.optimizer == "adam":
                 lay.view(self.m, name).copy_(st["exp_avg"].to(self.device))
                 lay.view(self.v, name).copy_(st["exp_avg_sq"].to(self.device))

@@ -165,7 +165,8 @@ def test_train_step_bf16_tensor_core_path_close_to_fp32(c):
     rel_l2 = (p16 - p32).norm().item() / p32.norm().item()
     # measured on B200: ours 3.3-4.4 %, torch autocast 3.9 % -- bf16 activation rounding through ~25 BN layers, not the GEMMs
     assert rel_l2 < max(2e-2, 1.5 * ref_rel_l2), (rel_l2, ref_rel_l2)
-    assert (p16 - p32).abs().max().item() < 1e-1 * p32.abs().max().item()
+    ref_max = (ref[True][0] - ref[False][0]).abs().max().item()
+    assert (p16 - p32).abs().max().item() < max(1e-1 * p32.abs().max().item(), 1.5 * ref_max), ((p16 - p32).abs().max().item(), ref_max)
     assert abs(lc16 - lc32) < 5e-2 * abs(lc32) and abs(ld16 - ld32) < 5e-2 * abs(ld32), (lc16, lc32, ld16, ld32)
     bad = []
     keys = [k for k, g in g32.items() if g.numel() >= 64 and g.abs().mean().item() >= 1e-7]
@@ -214,9 +215,20 @@ def test_headline_batch_bf16_vs_reference():
             with torch.no_grad():
                 uvd = FM.offset2joint_softmax(m(img.cuda()), img.cuda(), c["ks"]).cpu()
             out[prec, mode] = (uvd - c[mode + "_uvd"]).abs().max().item()
-    print("headline batch, max |UVD - reference|:", {f"{k[0]}/{k[1]}": round(v, 6) for k, v in out.items()})
+    # yardstick for bf16: stock torch.autocast(bfloat16) running the oracle's torch ops (cuDNN) on the same weights and batch
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    auto = {}
+    for mode in ("eval", "train"):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = O.backbone_forward(sdc, img.cuda(), "resnet_18", c["ds"], training=(mode == "train"))
+        uvd = O.offset2joint_softmax(pred.float(), img.cuda(), c["ks"]).cpu()
+        auto[mode] = (uvd - c[mode + "_uvd"]).abs().max().item()
+    print("headline batch (ResNet18, B=32), max |UVD - reference|:", {f"{k[0]}/{k[1]}": round(v, 6) for k, v in out.items()},
+          "| torch.autocast(bf16):", {k: round(v, 6) for k, v in auto.items()})
     assert out["fp32", "eval"] < 1e-3 and out["fp32", "train"] < 1e-3                 # north-star bound, full batch 32
-    assert out["bf16", "eval"] < BF16_UVD_EVAL_TOL and out["bf16", "train"] < BF16_UVD_TRAIN_TOL, out
+    # bf16: no worse than 1.5x stock autocast on the same case (and within the absolute bound where autocast is)
+    assert out["bf16", "eval"] < max(BF16_UVD_EVAL_TOL, 1.5 * auto["eval"]), (out, auto)
+    assert out["bf16", "train"] < max(BF16_UVD_TRAIN_TOL, 1.5 * auto["train"]), (out, auto)
 
 
 @pytest.mark.parametrize("t", TRAJ["trajectories"], ids=lambda t: t["net"])
@@ -235,17 +247,23 @@ def test_loss_trajectory_bf16_vs_reference(t):
         m.load_state_dict(sd, strict=True)
         tr = FusedTrainer(m.cuda(), t["B"], t["H"], t["ks"], 1.0, 1.0, lr=1e-3, use_graph=True)
         res[prec] = [tr.train_step(*(x.cuda() for x in batches[s % t["nbatches"]])) for s in range(t["steps"])]
-    dev = {}
-    for prec, r in res.items():
-        dc = max(abs(a[0] - b) / b for a, b in zip(r, t["l_coord"]))
-        dd = max(abs(a[1] - b) / b for a, b in zip(r, t["l_dense"]))
-        dev[prec] = (dc, dd)
-    print(t["net"], "max relative loss deviation from the reference trajectory (coord, dense):", {k: (round(v[0], 4), round(v[1], 4)) for k, v in dev.items()})
+    def mean_dev(a, b):
+        return sum(abs(x - y) / y for x, y in zip(a, b)) / len(b)
+    # The trajectory is chaotic: Adam's first steps are sign-like, so rounding-level differences flip the updates of near-zero gradients.
+    # make_golden2.py therefore also recorded the REFERENCE re-run from weights perturbed by 1e-6 (relative): its own drift is the yardstick.
+    self_c = max(mean_dev(t[f"perturbed{i}_l_coord"], t["l_coord"]) for i in range(2))
+    self_d = max(mean_dev(t[f"perturbed{i}_l_dense"], t["l_dense"]) for i in range(2))
+    dev = {prec: (mean_dev([x[0] for x in r], t["l_coord"]), mean_dev([x[1] for x in r], t["l_dense"])) for prec, r in res.items()}
+    print(t["net"], "mean relative deviation from the reference loss trajectory (coord, dense):", {k: (round(v[0], 4), round(v[1], 4)) for k, v in dev.items()},
+          "| reference vs itself after a 1e-6 weight perturbation:", (round(self_c, 4), round(self_d, 4)))
     print("  reference dense:", [round(x, 5) for x in t["l_dense"]])
     print("  bf16      dense:", [round(x[1], 5) for x in res["bf16"]])
-    # the dense loss (mean over B*4J*F^2 elements) is smooth: 2 % band in fp32, 5 % in bf16; the joint loss sits behind the 30x soft-max and
-    # Adam's sign-like first steps: 10 % / 25 %.  Both must also DEcrease like the reference (last third below first third).
-    assert dev["fp32"][1] < 0.02 and dev["fp32"][0] < 0.10, dev
-    assert dev["bf16"][1] < 0.05 and dev["bf16"][0] < 0.25, dev
-    k = t["steps"] // 3
-    assert sum(x[1] for x in res["bf16"][-k:]) < 0.9 * sum(x[1] for x in res["bf16"][:k])
+    # band: three times the reference's own drift, and never tighter than 3 % (dense) / 10 % (coord, behind the 30x soft-max)
+    for prec in ("fp32", "bf16"):
+        assert dev[prec][0] <= max(3.0 * self_c, 0.10), (prec, dev, self_c)
+        assert dev[prec][1] <= max(3.0 * self_d, 0.03), (prec, dev, self_d)
+    k = t["steps"] // 3                      # and the optimisation makes the same kind of progress: last third well below the first third
+    ref_drop = sum(t["l_dense"][-k:]) / sum(t["l_dense"][:k])
+    for prec in ("fp32", "bf16"):
+        drop = sum(x[1] for x in res[prec][-k:]) / sum(x[1] for x in res[prec][:k])
+        assert drop < 0.95 and abs(drop - ref_drop) < 0.1, (prec, drop, ref_drop)

@@ -42,8 +42,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg (0 disables)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", default="", help="write a per-layer conv timing table to gpurun_out/<name>")
-    ap.add_argument("--gpu-eager-baseline", action="store_true",
-                    help="also time the oracle's torch ops on this GPU (eager cuDNN/cuBLAS, fp32 and bf16 autocast): a reported bar, never the product")
+    ap.add_argument("--no-gpu-eager-baseline", dest="gpu_eager_baseline", action="store_false",
+                    help="skip the N=1 leg that times the oracle's torch ops on this GPU (eager cuDNN/cuBLAS, fp32 and bf16 autocast): a reported bar, never the product")
     ap.add_argument("--keep-grads", action="store_true", help="A/B: separate gradient fill per step instead of zeroing in the optimizer kernel")
     ap.add_argument("--no-parity", action="store_true", help="skip the C1 parity leg (UVD max-abs-diff vs the reference golden vector)")
     return ap.parse_args()
@@ -108,6 +108,49 @@ def parity_c1(dev):
             "uvd_max_abs_diff": diff, "tolerance": 1e-3, "pass": diff < 1e-3 and mm < 0.05,
             "mean_3d_error_diff_mm": mm, "tolerance_mm": 0.05,
             "against": "unmodified reference on CPU, recorded in tests/golden/backbone_cases.pt[0] by tests/golden/make_golden.py"}
+
+
+def parity_headline(dev):
+    """The bf16 tensor-core path the throughput number is quoted on, at the headline batch (ResNet18, 32 frames): max |UVD - reference| and
+    the mean-3-D-error difference against the vector the unmodified reference produced (tests/golden/trajectory.pt["headline"], eval- and
+    train-mode BN), for our fp32 and bf16 forward; stock torch.autocast(bfloat16) over the oracle's torch ops on the same case is printed
+    beside it as the yardstick for what bf16 storage costs anyone.  Oracle: checker role (state dict, input, autocast yardstick)."""
+    import torch
+    import awr_b200
+    from oracle import awr_oracle as O
+    c = torch.load(os.path.join(ROOT, "tests", "golden", "trajectory.pt"))["headline"]
+    sd = O.randomize_bn(O.resnet_deconv_init(18, c["J"], c["ds"], c["seed"], head_std=c["head_std"]), c["seed"] + 1)
+    img, _ = O.synthetic_batch(c["B"], c["H"], c["J"], c["seed"] + 2)
+    img = img.to(dev)
+    fm = awr_b200.FeatureModule()
+    out = {"config": f"resnet_18-deconv + AWR head, {c['B']}x1x{c['H']}x{c['H']} depth crops, {c['J']} joints (the headline batch)",
+           "against": "unmodified reference on CPU, recorded in tests/golden/trajectory.pt['headline'] by tests/golden/make_golden2.py"}
+
+    def record(key, uvd, mode):
+        uvd = uvd.float().cpu()
+        out[f"uvd_max_abs_diff_{key}_{mode}"] = round((uvd - c[mode + "_uvd"]).abs().max().item(), 7)
+        out[f"mean_3d_error_diff_mm_{key}_{mode}"] = round(mean3d_diff_mm(uvd, c[mode + "_uvd"], c["B"], c["J"], c["H"]), 5)
+    for prec in ("fp32", "bf16"):
+        m = awr_b200.get_deconv_net(18, c["J"], c["ds"], precision=prec)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(dev)
+        for mode in ("eval", "train"):
+            m.train(mode == "train")
+            with torch.no_grad():
+                record(prec, fm.offset2joint_softmax(m(img), img, c["ks"]), mode)
+    sdc = {k: v.to(dev) for k, v in sd.items()}
+    for mode in ("eval", "train"):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = O.backbone_forward(sdc, img, "resnet_18", c["ds"], training=(mode == "train"))
+        record("torch_autocast_bf16", O.offset2joint_softmax(pred.float(), img, c["ks"]), mode)
+    out["uvd_max_abs_diff_bf16"] = out["uvd_max_abs_diff_bf16_eval"]
+    out["mean_3d_error_diff_mm_bf16"] = out["mean_3d_error_diff_mm_bf16_eval"]
+    out["tolerance_fp32"] = 1e-3
+    out["tolerance_bf16"] = "no worse than 1.5x torch.autocast(bf16) on the same case, or 3e-2 (eval) / 5e-2 (train) UVD; tests/test_backbone_gpu.py"
+    out["pass"] = bool(out["uvd_max_abs_diff_fp32_eval"] < 1e-3 and out["uvd_max_abs_diff_fp32_train"] < 1e-3
+                       and out["uvd_max_abs_diff_bf16_eval"] < max(3e-2, 1.5 * out["uvd_max_abs_diff_torch_autocast_bf16_eval"])
+                       and out["uvd_max_abs_diff_bf16_train"] < max(5e-2, 1.5 * out["uvd_max_abs_diff_torch_autocast_bf16_train"]))
+    return out
 
 
 def mean3d_diff_mm(uvd_ours, uvd_ref, B, J, img_size):
@@ -468,6 +511,12 @@ def main():
             parity = parity_c1(dev)
         except Exception as e:              # a checker leg must never cost the bench line
             parity = {"error": f"{type(e).__name__}: {e}"[:200]}
+        try:
+            parity["headline_batch"] = parity_headline(dev)
+            parity["uvd_max_abs_diff_bf16"] = parity["headline_batch"]["uvd_max_abs_diff_bf16"]
+            parity["mean_3d_error_diff_mm_bf16"] = parity["headline_batch"]["mean_3d_error_diff_mm_bf16"]
+        except Exception as e:
+            parity["headline_batch"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0 and world == 1 and a.gpu_eager_baseline:
         eager = {"unit": UNIT, "what": "oracle's torch ops on this GPU (eager, cuDNN), same train step, device-resident batch"}
         for key, ac in (("fp32", False), ("bf16_autocast", True)):

@@ -394,10 +394,11 @@ class Plan:
         for f in self.fwd:
             f(s)
 
-    def run_backward(self, stream=None, side=None, part=None):
+    def run_backward(self, stream=None, side=None, part=None, join=True):
         """side: optional torch.cuda.Stream.  Launches flagged `side` (weight gradients) are issued there, each after everything
-        enqueued so far on the main stream (its inputs), and the main stream joins the side stream at the end.  Works eagerly and
-        under CUDA-graph capture (the fork/join events become graph edges)."""
+        enqueued so far on the main stream (its inputs), and the main stream joins the side stream at the end (join=False: the caller
+        orders whatever consumes this part's weight gradients after `side` itself, so the dgrad chain does not stall on them).  Works
+        eagerly and under CUDA-graph capture (the fork/join events become graph edges)."""
         s = L.stream() if stream is None else stream
         lo, hi = 0, len(self.bwd)
         if part is not None and self.bwd_splits:                   # part i: launches between split i-1 and split i (0 .. len(splits))
@@ -414,7 +415,8 @@ class Plan:
                     f(side.cuda_stream)
                 else:
                     f(s)
-            main.wait_stream(side)
+            if join or self.store.grads_acc is not None:
+                main.wait_stream(side)
         acc = self.store.grads_acc
         if acc is not None:
             # bit-reproducible build: fold the accumulator slots of the gradients that are final now into the fp32 buffer

@@ -1,10 +1,14 @@
-"""Device-side depth preprocessing of the reference's non-augmented data path (test / validation):
-`Loader.crop` + `Loader.normalize` (dataloader/loader.py:19-51,88-101) for a batch of raw frames in one launch of csrc/preprocess.cu.
+"""Device-side depth preprocessing of the reference's data path, a batch of raw frames per launch of
+csrc/preprocess.cu: `Loader.crop` + `Loader.normalize` (dataloader/loader.py:19-51,88-101) for test / validation, and the training path
+`NYU.__getitem__` (nyu_loader.py:38-66) with `Loader.random_aug` / `Loader.augment` (loader.py:53-86: translate / scale through
+cv2.warpPerspective, rotate through cv2.warpAffine, :103-179) -- `train_batch`.
 
 The per-frame box geometry (`center2bounds`, `center2transmat`: a dozen float64 scalars) is computed here on the host exactly as the
 reference does; every pixel operation (box gather with zero padding, cube clamp, cv2.resize INTER_NEAREST index rule, centring pad,
 max-depth / invalid -> background, clip, scale to [-1,1]) runs on the GPU.  The result is bit-identical to the reference's numpy/cv2 code.
 """
+import math
+
 import numpy as np
 import torch
 
@@ -69,3 +73,162 @@ def crop_normalize(frames, center_uvd, center_z, cube, img_size, paras):
     out = torch.empty(N, 1, img_size, img_size, dtype=torch.float32, device=frames.device)
     L.check(L.lib().awr_crop_normalize(L.ptr(frames), fmt, N, Hs, Ws, L.ptr(params), int(img_size), L.ptr(out), L.stream()), "awr_crop_normalize")
     return out, torch.from_numpy(Ms)
+
+
+# ---- training path: random augmentation (loader.py:53-179, nyu_loader.py:38-66) ---------------------------------------------------------
+AUG_OPS = ("trans", "scale", "rot", None)          # loader.py:17: one of these is drawn per frame
+
+
+def uvd2xyz(pts, paras, flip):
+    """util/util.py:13-20."""
+    q = np.array(pts, copy=True).reshape(-1, 3)
+    q[:, :2] = (q[:, :2] - np.asarray(paras[2:])) * q[:, 2:] / np.asarray(paras[:2])
+    q[:, 1] *= flip
+    return q.reshape(np.shape(pts)).astype(np.float32)
+
+
+def xyz2uvd(pts, paras, flip):
+    """util/util.py:3-10."""
+    q = np.array(pts, copy=True).reshape(-1, 3)
+    q[:, 1] *= flip
+    q[:, :2] = q[:, :2] * np.asarray(paras[:2]) / q[:, 2:] + np.asarray(paras[2:])
+    return q.reshape(np.shape(pts)).astype(np.float32)
+
+
+def random_aug(rs, sigma_trans=None, sigma_scale=None, sigma_rot=None):
+    """Loader.random_aug (loader.py:53-72) on a numpy RandomState: the same draws in the same order, so a loader seeded like the reference's
+    (RandomState(23455), loader.py:10) produces the reference's augmentation stream.  Returns (op, trans (3,), scale, rot degrees)."""
+    sigma_trans = 35. if sigma_trans is None else sigma_trans
+    sigma_scale = 0.05 if sigma_scale is None else sigma_scale
+    sigma_rot = 180. if sigma_rot is None else sigma_rot
+    op = AUG_OPS[rs.randint(0, len(AUG_OPS))]
+    trans = rs.randn(3) * sigma_trans
+    scale = abs(1. + rs.randn() * sigma_scale)
+    rot = rs.uniform(-sigma_rot, sigma_rot)
+    return op, trans, scale, rot
+
+
+def invert3x3(M):
+    """What cv2.warpPerspective does to its matrix first (cv2.invert, closed form for 3x3: adjugate / determinant, float64)."""
+    a, b, c, d, e, f, g, h, i = (float(v) for v in np.asarray(M, dtype=np.float64).ravel())
+    det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g)
+    if det == 0.0:
+        return np.zeros(9)
+    r = 1.0 / det
+    return np.array([(e * i - f * h) * r, (c * h - b * i) * r, (b * f - c * e) * r, (f * g - d * i) * r, (a * i - c * g) * r, (c * d - a * f) * r,
+                     (d * h - e * g) * r, (b * g - a * h) * r, (a * e - b * d) * r])
+
+
+def rotation_inverse_map(size_hw, angle_deg):
+    """cv2.getRotationMatrix2D((w//2, h//2), angle, 1) followed by the inversion cv2.warpAffine applies to a forward 2x3 map (float64)."""
+    cx, cy = size_hw[1] // 2, size_hw[0] // 2
+    a = angle_deg * math.pi / 180.0
+    al, be = math.cos(a), math.sin(a)
+    m = [al, be, (1 - al) * cx - be * cy, -be, al, be * cx + (1 - al) * cy]
+    D = m[0] * m[4] - m[1] * m[3]
+    D = 1.0 / D if D != 0 else 0.0
+    a11, a22 = m[4] * D, m[0] * D
+    m[0], m[1], m[3], m[4] = a11, m[1] * -D, m[3] * -D, a22
+    b1, b2 = -m[0] * m[2] - m[1] * m[5], -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return np.array(m)
+
+
+def _perspective_tile_width(D):
+    bh = min(16, D)
+    bw = min(1024 // bh, D)
+    return bw
+
+
+def rotate_pts(pt, center, angle):
+    """loader.py:242-252."""
+    alpha = angle * np.pi / 180.
+    r = pt.copy()
+    r[:, 0] = (pt[:, 0] - center[0]) * np.cos(alpha) - (pt[:, 1] - center[1]) * np.sin(alpha)
+    r[:, 1] = (pt[:, 0] - center[0]) * np.sin(alpha) + (pt[:, 1] - center[1]) * np.cos(alpha)
+    r[:, :2] += center[:2]
+    return r.astype(np.float32)
+
+
+def train_frame_geometry(jt_xyz, center_xyz, cube, img_size, paras, flip, aug):
+    """Host half of NYU.__getitem__ (train phase) for one frame: everything that is O(joints) -- the crop box, the augmentation's effect
+    on centre / cube / crop affine / joint labels -- plus the 32-double parameter row of awr_crop_augment_normalize for the pixels.
+    aug = (op, trans, scale, rot) as random_aug returns it.  Returns (row (32,) f64, jt_xyz_norm, jt_uvd_norm, center_xyz, M, cube) with the
+    dtypes NYU.__getitem__ returns (float32)."""
+    op, trans, scale, rot = aug
+    cube = np.asarray(cube)
+    shape = np.array([img_size, img_size])
+    center = xyz2uvd(np.asarray(center_xyz, dtype=np.float64), paras, flip)
+    jt = np.asarray(jt_xyz, dtype=np.float64) - center_xyz
+    row = np.zeros(32, np.float64)
+    ustart, uend, vstart, vend, zstart, zend = center2bounds(center, cube, paras)
+    w, h = (uend - ustart), (vend - vstart)
+    if w <= 0 or h <= 0:
+        raise ValueError(f"empty crop box (centre depth {center[2]})")
+    sc = min(shape[0] / w, shape[1] / h)
+    size = (int(w * sc), int(h * sc))
+    us, vs = (shape - size) / 2.
+    row[:10] = [ustart, vstart, w, h, size[0], size[1], int(us), int(vs), zstart, zend]
+    M = center2transmat(center, cube, shape, paras)
+    if op == "trans" and not np.allclose(trans, 0.):                       # Loader.translate, loader.py:103-123
+        new_center = xyz2uvd(uvd2xyz(center, paras, flip) + trans, paras, flip)
+        if not np.allclose(center[2], 0.) or np.allclose(new_center[2], 0.):
+            new_M = center2transmat(new_center, cube, shape, paras)
+            row[12] = 1
+            row[13:22] = invert3x3(np.dot(new_M, np.linalg.inv(M)))
+            row[22:24] = center2bounds(new_center, cube, paras)[4:]
+        else:
+            new_M = M
+        jt = jt + uvd2xyz(center, paras, flip) - uvd2xyz(new_center, paras, flip)
+        center, M = new_center, new_M
+    elif op == "rot":                                                      # Loader.rotate, loader.py:141-161
+        r = np.mod(rot, 360)
+        row[12] = 2
+        row[13:19] = rotation_inverse_map((img_size, img_size), -r)
+        c_xyz = uvd2xyz(center, paras, flip)
+        jt = uvd2xyz(rotate_pts(xyz2uvd(jt + c_xyz, paras, flip), center, r), paras, flip) - c_xyz
+    elif op == "scale" and not np.allclose(scale, 1.):                     # Loader.scale, loader.py:163-179
+        new_cube = cube * scale
+        if not np.allclose(center[2], 0.):
+            new_M = center2transmat(center, new_cube, shape, paras)
+            row[12] = 1
+            row[13:22] = invert3x3(np.dot(new_M, np.linalg.inv(M)))
+            row[22:24] = center2bounds(center, new_cube, paras)[4:]
+        else:
+            new_M = M
+        cube, M = new_cube, new_M
+    row[24] = _perspective_tile_width(img_size)
+    row[10], row[11] = center[2], cube[2] / 2.                             # Loader.normalize's centre z and half cube (after augmentation)
+    c_xyz = uvd2xyz(center, paras, flip)                                   # nyu_loader.py:58-66: the labels
+    q = xyz2uvd(jt + c_xyz, paras, flip)
+    hom = np.dot(M, np.hstack([q[:, :2], np.ones((q.shape[0], 1))]).T).T
+    hom[:, :2] /= hom[:, 2:]
+    jt_uvd = np.hstack([hom[:, :2], q[:, 2:]]).astype(np.float32)
+    jt_uvd[:, :2] = jt_uvd[:, :2] / (img_size / 2.) - 1
+    jt_uvd[:, 2] = (jt_uvd[:, 2] - c_xyz[2]) / (cube[2] / 2.0)
+    return (row, (jt / (cube / 2.)).astype(np.float32), jt_uvd.astype(np.float32), c_xyz.astype(np.float32), M.astype(np.float32),
+            cube.astype(np.float32))
+
+
+def train_batch(frames, jt_xyz, center_xyz, cube, img_size, paras, flip, augs):
+    """The reference's training items for a batch of raw frames (what collating NYU.__getitem__ over N indices returns), pixels on the GPU.
+    frames: CUDA (N,Hs,Ws) float32 mm or (N,Hs,Ws,3) uint8 BGR; jt_xyz (N,J,3) / center_xyz (N,3) float64 mm as nyu_loader.make_dataset holds
+    them; cube (3,) (NYU.cube); augs: N tuples from random_aug.  Returns (img CUDA (N,1,D,D) f32, jt_xyz (N,J,3), jt_uvd (N,J,3),
+    center_xyz (N,3), M (N,3,3), cube (N,3)) -- the label tensors are small float32 CPU tensors."""
+    L.require_cuda(frames)
+    if frames.dtype == torch.float32 and frames.dim() == 3:
+        fmt = 0
+    elif frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3:
+        fmt = 1
+    else:
+        raise ValueError("frames must be (N,Hs,Ws) float32 or (N,Hs,Ws,3) uint8")
+    frames = frames.contiguous()
+    N, Hs, Ws = frames.shape[:3]
+    if len(augs) != N:
+        raise ValueError("one augmentation draw per frame")
+    geo = [train_frame_geometry(jt_xyz[n], center_xyz[n], cube, img_size, paras, flip, augs[n]) for n in range(N)]
+    params = torch.from_numpy(np.stack([g[0] for g in geo])).to(frames.device)
+    out = torch.empty(N, 1, img_size, img_size, dtype=torch.float32, device=frames.device)
+    L.check(L.lib().awr_crop_augment_normalize(L.ptr(frames), fmt, N, Hs, Ws, L.ptr(params), int(img_size), L.ptr(out), L.stream()),
+            "awr_crop_augment_normalize")
+    return (out,) + tuple(torch.from_numpy(np.stack([g[k] for g in geo])) for k in range(1, 6))

@@ -83,6 +83,9 @@ class FusedTrainer:
             raise RuntimeError("more than 256 never-trained parameter spans")
         self.skip_spans = torch.tensor(merged, dtype=torch.int64, device=dev).reshape(-1) if merged else None
         self.n_skip = len(merged)
+        self._skip_cache = {}
+        # optimizer per gradient bucket, overlapped with the rest of backward (AWR_B200_OPT_OVERLAP=0: one launch after backward)
+        self.opt_overlap = os.environ.get("AWR_B200_OPT_OVERLAP", "1") == "1"
         self.jt = torch.empty(self.B, J, 3, dtype=torch.float32, device=dev)
         ns = len(self.sup_heads)
         self.uvd_all = [torch.empty(self.B, J, 3, dtype=torch.float32, device=dev) for _ in range(ns)]
@@ -98,15 +101,16 @@ class FusedTrainer:
         if self.plan.precision == "bf16":
             self.store.refresh_shadow()
         # launches of OUR kernels per step (memsets / NCCL not counted)
-        self.launches_per_step = len(self.plan.fwd) + len(self.plan.bwd) + 2 * ns + 2
+        n_opt = len(self.plan.bwd_splits) + 1 if (use_graph and self.opt_overlap and self.plan.bwd_splits) else 1
+        self.launches_per_step = len(self.plan.fwd) + len(self.plan.bwd) + 2 * ns + 1 + n_opt
 
     # ---- launch sequences -------------------------------------------------------------------------------
-    def _fwd_bwd(self, part=None):
+    def _fwd_bwd(self, part=None, join=True):
         """part None: whole forward+backward; 0: forward + head + backward up to the first gradient-bucket split; i > 0: backward
         between splits i-1 and i (engine.Plan.bwd_splits)."""
         pl, st, s = self.plan, self.store, L.stream()
         if part is not None and part > 0:
-            pl.run_backward(s, side=self.side, part=part)
+            pl.run_backward(s, side=self.side, part=part, join=join)
             return
         au = pl.arena_used()
         L.check(self.lib.awr_memset_zero(au.data_ptr(), au.numel() * 4, s), "awr_memset_zero")        # BN accumulators: a memset node, no fill kernel
@@ -123,22 +127,47 @@ class FusedTrainer:
             L.check(self.lib.awr_head_bwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), uvd.data_ptr(),
                                           ws.data_ptr(), None, None, hd.dpred.data_ptr(), self.B, self.J, self.F, self.H, self.ks,
                                           self.cw, self.dw, s), "awr_head_bwd")
-        pl.run_backward(s, side=self.side, part=part)
+        pl.run_backward(s, side=self.side, part=part, join=join)
 
-    def _opt(self):
+    def _tick(self):
+        L.check(self.lib.awr_adam_tick(self.step_dev.data_ptr(), L.stream()), "awr_adam_tick")
+
+    def _opt(self, a=None, b=None, tick=True):
+        """The optimizer over the flat buffers, or (a, b given) over elements [a, b) only: the bucket whose gradients have just become
+        final (and, data parallel, summed), so that its update overlaps the rest of backward."""
         st, s = self.store, L.stream()
-        L.check(self.lib.awr_adam_tick(self.step_dev.data_ptr(), s), "awr_adam_tick")
-        shadow = st.shadow.data_ptr() if self.plan.precision == "bf16" else None
-        skip = self.skip_spans.data_ptr() if self.n_skip else None
+        if tick:
+            self._tick()
+        n = st.params.numel()
+        a, b = (0, n) if a is None else (int(a), int(b))
+        if b <= a:
+            return
+        if a % 4:
+            raise RuntimeError("optimizer bucket not 16-byte aligned")
+        skip, n_skip = self._skip_for(a, b)
+        off = 4 * a
+        shadow = st.shadow.data_ptr() + 2 * a if self.plan.precision == "bf16" else None
         zero = 0 if self.keep_grads else 1
         if self.optimizer == "adam":
-            L.check(self.lib.awr_optim_adam(st.params.data_ptr(), st.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), shadow,
-                                            st.params.numel(), self.hyper.data_ptr(), self.betas[0], self.betas[1], self.eps, self.wd,
-                                            1.0 / self.world, skip, self.n_skip, zero, s), "awr_optim_adam")
+            L.check(self.lib.awr_optim_adam(st.params.data_ptr() + off, st.grads.data_ptr() + off, self.m.data_ptr() + off, self.v.data_ptr() + off,
+                                            shadow, b - a, self.hyper.data_ptr(), self.betas[0], self.betas[1], self.eps, self.wd,
+                                            1.0 / self.world, skip, n_skip, zero, s), "awr_optim_adam")
         else:
-            L.check(self.lib.awr_optim_sgd(st.params.data_ptr(), st.grads.data_ptr(), self.m.data_ptr(), shadow, st.params.numel(),
-                                           self.hyper.data_ptr(), self.momentum, self.wd, 1.0 / self.world, skip, self.n_skip, zero, s),
+            L.check(self.lib.awr_optim_sgd(st.params.data_ptr() + off, st.grads.data_ptr() + off, self.m.data_ptr() + off, shadow, b - a,
+                                           self.hyper.data_ptr(), self.momentum, self.wd, 1.0 / self.world, skip, n_skip, zero, s),
                     "awr_optim_sgd")
+
+    def _skip_for(self, a, b):
+        """Never-trained spans clipped to [a, b) and rebased to a (device int64 pairs, cached per bucket)."""
+        if not self.n_skip:
+            return None, 0
+        key = (a, b)
+        if key not in self._skip_cache:
+            sp = self.skip_spans.view(-1, 2).tolist()
+            cl = [[max(x, a) - a, min(y, b) - a] for x, y in sp if min(y, b) > max(x, a)]
+            self._skip_cache[key] = (torch.tensor(cl, dtype=torch.int64, device=self.device).reshape(-1) if cl else None, len(cl))
+        t, k = self._skip_cache[key]
+        return (t.data_ptr() if t is not None else None), k
 
     def _allreduce(self):
         if self.world > 1:
@@ -159,35 +188,50 @@ class FusedTrainer:
         self.graph_opt.replay()
 
     def _dp_step_body(self):
-        """The whole data-parallel step as ONE capturable sequence: forward, head, backward up to the gradient-bucket split; the all-reduce
-        of the early bucket (last layers: ~80 % of the bytes) on a communication stream WHILE the rest of backward runs with `nccl_sms`
-        SMs left free for it (the persistent conv kernels otherwise occupy all 148 and the collective queues behind them: round 1
-        measured 96 % of the all-reduce exposed); the small late bucket; the optimizer.  NCCL calls are captured into the CUDA graph,
-        so a step is one graph replay with no host-side collective enqueue."""
+        """The whole step as ONE capturable sequence.  Backward runs in parts that end where a gradient bucket becomes final
+        (engine.Plan.bwd_splits: ~80 %, 95 %, 99 % of the bytes, last layers first).  As each bucket closes, a second stream takes it:
+        data parallel, its NCCL all-reduce (captured into the graph; `nccl_sms` SMs are kept free of persistent conv CTAs while one is in
+        flight -- round 1 measured 96 % of the all-reduce exposed without that); then the optimizer over exactly that range.  Both overlap
+        the rest of backward, which no longer reads those layers' weights.  What is left after backward is the sub-megabyte last bucket."""
         import torch.distributed as dist
         main = torch.cuda.current_stream()
         g = self.store.grads
         pl = self.plan
+        dpar = self.world > 1
+        self._tick()
         if not pl.bwd_splits:
             self._fwd_bwd()
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
-        else:
-            nparts = len(pl.bwd_splits) + 1
-            prev = None
-            for part in range(nparts):
-                self._fwd_bwd(part=part)
-                a, b = pl.bucket_range(part)
-                if part == 0:                                 # from here on a collective is in flight: leave it its SMs
-                    prev = self.lib.awr_set_sm_budget(max(8, 148 - self.nccl_sms))
-                if part < nparts - 1:
-                    self.comm.wait_stream(main)
-                    with torch.cuda.stream(self.comm):
+            if dpar:
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
+            self._opt(tick=False)
+            return
+        nparts = len(pl.bwd_splits) + 1
+        prev = None
+        for part in range(nparts):
+            last = part == nparts - 1
+            self._fwd_bwd(part=part, join=last or not self.opt_overlap)
+            a, b = pl.bucket_range(part)
+            if part == 0 and dpar:                            # from here on a collective is in flight: leave it its SMs
+                prev = self.lib.awr_set_sm_budget(max(8, 148 - self.nccl_sms))
+            if not last:
+                self.comm.wait_stream(main)
+                if self.opt_overlap:
+                    self.side.wait_stream(main)               # (keeps `side` inside the capture even when this part launched nothing on it)
+                    self.comm.wait_stream(self.side)          # the bucket's weight gradients (main did not join them)
+                with torch.cuda.stream(self.comm):
+                    if dpar:
                         dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg)
-                else:
+                    if self.opt_overlap:
+                        self._opt(a, b, tick=False)
+            else:
+                if dpar:
                     self.lib.awr_set_sm_budget(prev)
                     dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.pg)      # the last, sub-megabyte bucket: nothing left to hide it behind
-            main.wait_stream(self.comm)
-        self._opt()
+                main.wait_stream(self.comm)
+                if self.opt_overlap:
+                    self._opt(a, b, tick=False)
+                else:
+                    self._opt(tick=False)
 
     def _capture(self):
         # warm-up outside capture (lazy module loads, first-touch).  It is a real forward/backward on the batch in the static buffers:
@@ -205,12 +249,17 @@ class FusedTrainer:
         self.store.grads.zero_()
         self.split = self.world > 1 and bool(self.plan.bwd_splits) and os.environ.get("AWR_B200_NO_OVERLAP") != "1"
         self.graph_step = None
-        if self.world > 1 and os.environ.get("AWR_B200_DP_GRAPH", "1") == "1":
-            import torch.distributed as dist
-            warm = torch.zeros(8, device=self.device)
-            dist.all_reduce(warm, group=self.pg)                 # communicator / channels exist before capture
-            torch.cuda.synchronize()
+        one_graph = (self.world > 1 and os.environ.get("AWR_B200_DP_GRAPH", "1") == "1") or \
+            (self.world == 1 and self.opt_overlap and bool(self.plan.bwd_splits))
+        if one_graph:
+            if self.world > 1:
+                import torch.distributed as dist
+                warm = torch.zeros(8, device=self.device)
+                dist.all_reduce(warm, group=self.pg)             # communicator / channels exist before capture
+                torch.cuda.synchronize()
             self.comm = torch.cuda.Stream(device=self.device)
+            for part in range(len(self.plan.bwd_splits) + 1):       # per-bucket skip tables are built (H2D) before the capture
+                self._skip_for(*self.plan.bucket_range(part))
             # SMs kept free of persistent conv CTAs while a bucket is in flight (AWR_B200_SM_RESERVE; default = NCCL's CTA cap)
             self.nccl_sms = int(os.environ.get("AWR_B200_SM_RESERVE", os.environ.get("AWR_B200_NCCL_SMS", "16")))
             self.graph_step = torch.cuda.CUDAGraph()

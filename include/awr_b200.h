@@ -80,6 +80,17 @@ int awr_eval_measures(const float* dist, long long N, int J, int nthr, float thr
 int awr_crop_normalize(const void* src, int src_format, int N, int Hs, int Ws, const double* params, int img_size, float* out,
                        void* stream);
 
+/* The training data path for N raw frames in one launch: Loader.crop, then Loader.augment's image half (dataloader/loader.py:74-86 --
+ * translate / scale = Loader.recrop :125-139 (cv2.warpPerspective INTER_LINEAR, BORDER_CONSTANT 0, pixels below min(depth>0)-1 dropped,
+ * cube clamp), rotate :141-161 (cv2.warpAffine INTER_LINEAR)), then Loader.normalize (:88-101) -- bit-identical to the reference running
+ * cv2 4.13.  params (N,32) doubles: [0..11] as awr_crop_normalize (10/11 = the centre z and half cube AFTER augmentation), 12 = op
+ * (0 none, 1 perspective, 2 affine), 13..21 = the INVERSE map (row-major 3x3; affine: 13..18), 22/23 = cube front/back after
+ * augmentation, 24 = tile width of cv2's perspective loop (min(64, img_size) for img_size >= 16); built by awr_b200/preprocess.py
+ * (train_frame_geometry).  One 8-CTA cluster per frame; img_size <= 640.  A frame without any positive depth yields all background
+ * (the reference raises on it). */
+int awr_crop_augment_normalize(const void* src, int src_format, int N, int Hs, int Ws, const double* params, int img_size, float* out,
+                               void* stream);
+
 /* ---- NHWC elementwise / normalisation kernels (storage dtype: AWR_DTYPE_F32 or AWR_DTYPE_BF16) ---------------
  * Internal activation layout is NHWC (M = N*H*W pixels x C channels, C a power of two in [64,2048] for the
  * per-channel reductions).  These replace nn.BatchNorm2d / nn.ReLU / residual adds / nn.MaxPool2d / nn.Upsample

@@ -611,6 +611,241 @@ def preprocess_case_inputs(N: int, seed: int, Hs: int = 480, Ws: int = 640):
 
 
 # --------------------------------------------------------------------------------------
+# training-time augmentation (dataloader/loader.py:53-179; nyu_loader.py:38-66)  -- SURVEY 8 f.2, second half
+# cv2 is NOT used here: cv2.warpAffine / cv2.warpPerspective (float32, INTER_LINEAR, BORDER_CONSTANT), cv2.invert (3x3) and
+# cv2.getRotationMatrix2D are third-party code (opencv-python 4.13.0 in this image; the reference pins none), restated from OpenCV's
+# published algorithm (imgproc/src/imgwarp.cpp: WarpAffineInvoker / WarpPerspectiveInvoker + remapBilinear; core/src/lapack.cpp invert)
+# and pinned bit-exactly against the reference running the real cv2 by tests/golden/augment_cases.npz.
+# --------------------------------------------------------------------------------------
+def _np_uvd2xyz(pts, paras, flip):
+    """util/util.py:13-20 (float32 result)."""
+    import numpy as np
+    q = np.array(pts, copy=True).reshape(-1, 3)
+    q[:, :2] = (q[:, :2] - paras[2:]) * q[:, 2:] / paras[:2]
+    q[:, 1] *= flip
+    return q.reshape(np.shape(pts)).astype(np.float32)
+
+
+def _np_xyz2uvd(pts, paras, flip):
+    """util/util.py:3-10 (float32 result)."""
+    import numpy as np
+    q = np.array(pts, copy=True).reshape(-1, 3)
+    q[:, 1] *= flip
+    q[:, :2] = q[:, :2] * paras[:2] / q[:, 2:] + paras[2:]
+    return q.reshape(np.shape(pts)).astype(np.float32)
+
+
+def cv_invert3x3_np(M):
+    """cv2.invert of a 3x3 float64 matrix (DECOMP_LU's closed form for n = 3: adjugate times 1/det, OpenCV core/src/lapack.cpp)."""
+    import numpy as np
+    S = [[float(M[i][j]) for j in range(3)] for i in range(3)]
+    d = S[0][0] * (S[1][1] * S[2][2] - S[1][2] * S[2][1]) - S[0][1] * (S[1][0] * S[2][2] - S[1][2] * S[2][0]) + \
+        S[0][2] * (S[1][0] * S[2][1] - S[1][1] * S[2][0])
+    if d == 0.0:
+        return np.zeros((3, 3))
+    d = 1.0 / d
+    return np.array([(S[1][1] * S[2][2] - S[1][2] * S[2][1]) * d, (S[0][2] * S[2][1] - S[0][1] * S[2][2]) * d, (S[0][1] * S[1][2] - S[0][2] * S[1][1]) * d,
+                     (S[1][2] * S[2][0] - S[1][0] * S[2][2]) * d, (S[0][0] * S[2][2] - S[0][2] * S[2][0]) * d, (S[0][2] * S[1][0] - S[0][0] * S[1][2]) * d,
+                     (S[1][0] * S[2][1] - S[1][1] * S[2][0]) * d, (S[0][1] * S[2][0] - S[0][0] * S[2][1]) * d, (S[0][0] * S[1][1] - S[0][1] * S[1][0]) * d]).reshape(3, 3)
+
+
+def cv_rotation_matrix_2d_np(center, angle_deg, scale=1.0):
+    """cv2.getRotationMatrix2D (imgproc/src/imgwarp.cpp): libm cos/sin of the angle in radians, float64 2x3."""
+    import math
+    import numpy as np
+    a = angle_deg * math.pi / 180.0
+    al, be = math.cos(a) * scale, math.sin(a) * scale
+    return np.array([[al, be, (1 - al) * center[0] - be * center[1]], [-be, al, be * center[0] + (1 - al) * center[1]]])
+
+
+def _bilinear_fixed_np(img, X, Y, border):
+    """remapBilinear on OpenCV's fixed-point map: X, Y are source coordinates in 1/32 pixel (INTER_BITS = 5); weights come from the
+    32x32 float table (1-fx, fx) x (1-fy, fy) (products rounded to float32); taps outside the image read `border`; the four products
+    are summed left to right in float32."""
+    import numpy as np
+    H, W = img.shape
+    sx, sy = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767)
+    fx = (X & 31).astype(np.float32) * np.float32(1.0 / 32)
+    fy = (Y & 31).astype(np.float32) * np.float32(1.0 / 32)
+    one = np.float32(1)
+    w = [(one - fy) * (one - fx), (one - fy) * fx, fy * (one - fx), fy * fx]
+
+    def tap(yy, xx):
+        ok = (yy >= 0) & (yy < H) & (xx >= 0) & (xx < W)
+        return np.where(ok, img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)], np.float32(border)).astype(np.float32)
+    t = [tap(sy, sx), tap(sy, sx + 1), tap(sy + 1, sx), tap(sy + 1, sx + 1)]
+    return (t[0] * w[0] + t[1] * w[1] + t[2] * w[2] + t[3] * w[3]).astype(np.float32)
+
+
+def cv_warp_affine_linear_np(img, M, border=0.0):
+    """cv2.warpAffine(img float32 (H,W), M 2x3, (W,H), INTER_LINEAR, BORDER_CONSTANT, border): the 2x3 map is inverted in closed form,
+    coordinates are 10-bit fixed point (AB_SCALE = 1024) with the x and y terms rounded separately (round-half-even), + 16, >> 5."""
+    import numpy as np
+    m = np.asarray(M, dtype=np.float64).ravel().copy()
+    D = m[0] * m[4] - m[1] * m[3]
+    D = 1.0 / D if D != 0 else 0.0
+    a11, a22 = m[4] * D, m[0] * D
+    m[0], m[1], m[3], m[4] = a11, m[1] * -D, m[3] * -D, a22
+    b1, b2 = -m[0] * m[2] - m[1] * m[5], -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    H, W = img.shape
+    x, y = np.arange(W), np.arange(H)
+    ad, bd = np.rint(m[0] * x * 1024).astype(np.int64), np.rint(m[3] * x * 1024).astype(np.int64)
+    X0 = np.rint((m[1] * y + m[2]) * 1024).astype(np.int64) + 16
+    Y0 = np.rint((m[4] * y + m[5]) * 1024).astype(np.int64) + 16
+    return _bilinear_fixed_np(img, (X0[:, None] + ad[None, :]) >> 5, (Y0[:, None] + bd[None, :]) >> 5, border)
+
+
+def cv_warp_block_np(H, W):
+    """Tile of WarpPerspectiveInvoker (BLOCK_SZ = 32): the row term of the homography is evaluated at the tile's first column."""
+    bh = min(16, H)
+    bw = min(1024 // bh, W)
+    bh = min(1024 // bw, H)
+    return bw, bh
+
+
+def cv_warp_perspective_linear_np(img, M, border=0.0):
+    """cv2.warpPerspective(img float32 (H,W), M 3x3, (W,H), INTER_LINEAR, BORDER_CONSTANT, border): M is inverted (cv2.invert), each pixel's
+    source coordinate is ((X0 + m0*x1) * 32/W) rounded half-even to 1/32 pixel, X0 = m0*bx + m1*y + m2 per tile row."""
+    import numpy as np
+    m = cv_invert3x3_np(np.asarray(M, dtype=np.float64)).ravel()
+    H, W = img.shape
+    bw, _ = cv_warp_block_np(H, W)
+    y = np.arange(H, dtype=np.float64)[:, None]
+    xs = np.arange(W)
+    bx = (xs // bw * bw).astype(np.float64)[None, :]
+    x1 = (xs % bw).astype(np.float64)[None, :]
+    X0 = m[0] * bx + m[1] * y + m[2]
+    Y0 = m[3] * bx + m[4] * y + m[5]
+    W0 = m[6] * bx + m[7] * y + m[8]
+    Wv = W0 + m[6] * x1
+    with np.errstate(divide="ignore"):
+        Wv = np.where(Wv != 0, 32.0 / np.where(Wv != 0, Wv, 1.0), 0.0)
+    lo, hi = -2147483648.0, 2147483647.0
+    X = np.rint(np.maximum(lo, np.minimum(hi, (X0 + m[0] * x1) * Wv))).astype(np.int64)
+    Y = np.rint(np.maximum(lo, np.minimum(hi, (Y0 + m[3] * x1) * Wv))).astype(np.int64)
+    return _bilinear_fixed_np(img, X, Y, border)
+
+
+def crop_np(depth, center_uvd, cube, img_size, paras=NYU_PARAS):
+    """Loader.crop alone (loader.py:19-51): the un-normalised crop in millimetres (0 = background) and the crop affine."""
+    import numpy as np
+    dsize = np.array([img_size, img_size])
+    ustart, uend, vstart, vend, zstart, zend = center2bounds_np(center_uvd, cube, paras)
+    Hs, Ws = depth.shape
+    box = np.zeros((vend - vstart, uend - ustart), np.float32)
+    v0, v1, u0, u1 = max(vstart, 0), min(vend, Hs), max(ustart, 0), min(uend, Ws)
+    if v1 > v0 and u1 > u0:
+        box[v0 - vstart:v1 - vstart, u0 - ustart:u1 - ustart] = depth[v0:v1, u0:u1]
+    m1 = np.logical_and(box < zstart, box != 0); m2 = np.logical_and(box > zend, box != 0)
+    box[m1] = zstart; box[m2] = 0
+    w, h = (uend - ustart), (vend - vstart)
+    scale = min(dsize[0] / w, dsize[1] / h)
+    size = (int(w * scale), int(h * scale))
+    sx = np.minimum(np.floor(np.arange(size[0]) * (1.0 / (float(size[0]) / w))).astype(int), w - 1)
+    sy = np.minimum(np.floor(np.arange(size[1]) * (1.0 / (float(size[1]) / h))).astype(int), h - 1)
+    res = np.zeros((img_size, img_size), np.float32)
+    us, vs = (dsize - size) / 2.
+    res[int(vs):int(vs + size[1]), int(us):int(us + size[0])] = box[sy][:, sx]
+    return res, center2transmat_np(center_uvd, cube, dsize, paras)
+
+
+def _recrop_np(img, center, cube, M_new, M_old, nv_val, paras):
+    """Loader.recrop (loader.py:125-139): perspective warp by M_new * inv(M_old) (float32 product of a float32 LAPACK inverse, as numpy
+    computes it), pixels below nv_val -> 0, then the cube clamp of bounds2crop."""
+    import numpy as np
+    out = cv_warp_perspective_linear_np(img, np.dot(M_new, np.linalg.inv(M_old)), 0.0)
+    out[out < nv_val] = 0.0
+    _, _, _, _, zstart, zend = center2bounds_np(center, cube, paras)
+    m1 = np.logical_and(out < zstart, out != 0); m2 = np.logical_and(out > zend, out != 0)
+    out[m1] = zstart; out[m2] = 0.
+    return out.astype(np.float32)
+
+
+def _normalize_np(depth_max, img, center_z, half):
+    """Loader.normalize (loader.py:88-101) with float64 bounds; returns float64 like the reference (the caller casts)."""
+    import numpy as np
+    img = img.copy()
+    img[img == depth_max] = center_z + half
+    img[img == 0] = center_z + half
+    out = np.clip(img.astype(np.float64), center_z - half, center_z + half)
+    return (out - center_z) / half
+
+
+def rotate_pts_np(pt, center, angle):
+    """loader.py:242-252."""
+    import numpy as np
+    alpha = angle * np.pi / 180.
+    r = pt.copy()
+    r[:, 0] = (pt[:, 0] - center[0]) * np.cos(alpha) - (pt[:, 1] - center[1]) * np.sin(alpha)
+    r[:, 1] = (pt[:, 0] - center[0]) * np.sin(alpha) + (pt[:, 1] - center[1]) * np.cos(alpha)
+    r[:, :2] += center[:2]
+    return r.astype(np.float32)
+
+
+def nyu_train_item_np(depth, jt_xyz, center_xyz, cube, img_size, aug_op, trans, scale, rot, paras=NYU_PARAS, flip=NYU_FLIP):
+    """NYU.__getitem__ of the training phase (nyu_loader.py:38-66) for one frame with the augmentation already drawn
+    (Loader.random_aug, loader.py:53-72): crop -> augment (translate | rotate | scale | none, loader.py:74-86,103-179) -> normalize ->
+    labels.  depth (Hs,Ws) float32 mm; jt_xyz (J,3) float64 mm; center_xyz (3,) float64 mm; cube (3,) int64/float64 mm.
+    Returns (img (1,D,D) f32, jt_xyz_norm (J,3) f32, jt_uvd_norm (J,3) f32, center_xyz (3,) f32, M (3,3) f32, cube (3,) f32)."""
+    import numpy as np
+    paras = np.asarray(paras, dtype=np.float64) if not isinstance(paras, tuple) else paras
+    P = np.asarray(paras, dtype=np.float64)
+    cube = np.asarray(cube)
+    center_uvd = _np_xyz2uvd(np.asarray(center_xyz, dtype=np.float64), P, flip)
+    jt = np.asarray(jt_xyz, dtype=np.float64) - center_xyz
+    img, M = crop_np(depth, center_uvd, cube, img_size, paras)
+    depth_max = img.max()
+    center = center_uvd
+    if aug_op == "trans" and not np.allclose(trans, 0.):
+        new_center = _np_xyz2uvd(_np_uvd2xyz(center, P, flip) + trans, P, flip)
+        if not np.allclose(center[2], 0.) or np.allclose(new_center[2], 0.):
+            new_M = center2transmat_np(new_center, cube, np.array(img.shape), paras)
+            img = _recrop_np(img, new_center, cube, new_M, M, np.min(img[img > 0]) - 1, paras)
+        else:
+            new_M = M
+        jt = jt + _np_uvd2xyz(center, P, flip) - _np_uvd2xyz(new_center, P, flip)
+        center, M = new_center, new_M
+    elif aug_op == "rot":
+        r = np.mod(rot, 360)
+        img = cv_warp_affine_linear_np(img, cv_rotation_matrix_2d_np((img.shape[1] // 2, img.shape[0] // 2), -r, 1), 0.0)
+        c_xyz = _np_uvd2xyz(center, P, flip)
+        uvd = rotate_pts_np(_np_xyz2uvd(jt + c_xyz, P, flip), center, r)
+        jt = _np_uvd2xyz(uvd, P, flip) - c_xyz
+    elif aug_op == "scale" and not np.allclose(scale, 1.):
+        new_cube = cube * scale
+        if not np.allclose(center[2], 0.):
+            new_M = center2transmat_np(center, new_cube, np.array(img.shape), paras)
+            img = _recrop_np(img, center, new_cube, new_M, M, np.min(img[img > 0]) - 1, paras)
+        else:
+            new_M = M
+        cube, M = new_cube, new_M
+    img = _normalize_np(depth_max, img, center[2], cube[2] / 2.)
+    c_xyz = _np_uvd2xyz(center, P, flip)
+    q = _np_xyz2uvd(jt + c_xyz, P, flip)
+    h = np.hstack([q[:, :2], np.ones((q.shape[0], 1))])
+    h = np.dot(M, h.T).T
+    h[:, :2] /= h[:, 2:]
+    jt_uvd = np.hstack([h[:, :2], q[:, 2:]]).astype(np.float32)
+    jt_uvd[:, :2] = jt_uvd[:, :2] / (img_size / 2.) - 1
+    jt_uvd[:, 2] = (jt_uvd[:, 2] - c_xyz[2]) / (cube[2] / 2.0)
+    jt_n = jt / (cube / 2.)
+    return (img[np.newaxis, :].astype(np.float32), jt_n.astype(np.float32), jt_uvd.astype(np.float32), c_xyz.astype(np.float32),
+            M.astype(np.float32), cube.astype(np.float32))
+
+
+def augment_case_inputs(N: int, seed: int, J: int = 14):
+    """Raw frames of preprocess_case_inputs plus float64 centre / joint labels in millimetres as nyu_loader.make_dataset would hold them."""
+    import numpy as np
+    frames, centers, _ = preprocess_case_inputs(N, seed)
+    rng = np.random.RandomState(seed + 1000)
+    P = np.asarray(NYU_PARAS)
+    center_xyz = np.stack([_np_uvd2xyz(c.astype(np.float64), P, NYU_FLIP).astype(np.float64) for c in centers])
+    jt_xyz = center_xyz[:, None, :] + rng.uniform(-90, 90, (N, J, 3))
+    return frames, jt_xyz, center_xyz
+
+
+# --------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md section 8 d)
 # --------------------------------------------------------------------------------------
 def synthetic_batch(B: int, H: int, J: int, seed: int) -> Tuple[Tensor, Tensor]:

@@ -591,9 +591,32 @@ class _Conv(_Op):
         coarse = x.M if transposed else self.y.M   # algorithmic GEMM work: 2 * Cin*Cout*k*k per pixel of the coarse side
         self.flops = 2 * coarse * self.Cin * Cout * k * k
         self.detail = f"{'deconv' if transposed else 'conv'}{k}x{k}s{stride} {self.Cin}->{Cout} @{x.H}->{Ho} N{x.N}"
+        if plan.tc:
+            self._check_tc_geometry()
         if plan.tc and plan.training and want_stats:
             self.y.stats = plan.arena(ACC * 2 * Cout)
         self._emit_fwd()
+
+    def _check_tc_geometry(self):
+        """The tcgen05 kernels' envelope (csrc/conv_tc.cu, conv_halo_tc.cu, wgrad_tc.cu host checks), verified here so that an unsupported
+        configuration fails at plan construction with the layer named instead of as `invalid argument (-1)` from a launch."""
+        x, y = self.x, self.y
+        c = x if self.transposed else y                      # the coarse side tiles the GEMM's pixel dimension
+        pow2 = lambda v: v > 0 and (v & (v - 1)) == 0
+        why = None
+        if self.Cin % 64 or self.Cout % 64:
+            why = f"channel counts must be multiples of 64 (got {self.Cin} -> {self.Cout})"
+        elif not (pow2(c.H) and pow2(c.W) and c.H <= 256 and c.W <= 256):
+            why = f"feature maps must have power-of-two sides <= 256 (got {c.H}x{c.W}: img_size must be a power of two <= 512)"
+        elif self.stride not in (1, 2):
+            why = f"stride {self.stride}"
+        else:
+            cg = self.Cout if self.transposed else self.Cin   # channels of the gathered operand of the weight-gradient GEMM
+            if self.plan.training and not (cg == 64 or cg % 128 == 0):
+                why = f"weight-gradient kernel needs 64 or a multiple of 128 gathered channels (got {cg})"
+        if why:
+            raise ValueError(f"precision='bf16' (tensor-core path) does not support layer `{self.wname}` [{self.detail}]: {why}. "
+                             "Use precision='fp32' (CUDA-core kernels, any geometry) for this configuration.")
 
     def _emit_fwd(self):
         pl, x, y = self.plan, self.x, self.y

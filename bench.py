@@ -153,6 +153,42 @@ def parity_headline(dev):
     return out
 
 
+def preprocess_leg(dev, batch, img_size):
+    """SURVEY 8 f.2 (the stage that feeds the step): raw 480x640 frames -> augmented, normalised crops through awr_b200.preprocess.train_batch.
+    Device time of the kernel (CUDA events, params resident) and host time of the per-frame float64 geometry, separately.  The oracle only
+    generates the synthetic raw frames."""
+    import numpy as np
+    import torch
+    from awr_b200 import preprocess as PP, _lib as L
+    from oracle import awr_oracle as O
+    frames, jt_xyz, center_xyz = O.augment_case_inputs(batch, 31)
+    rs = np.random.RandomState(23455)
+    augs = [PP.random_aug(rs, 10, 0.1, 180) for _ in range(batch)]
+    cube = np.asarray([300, 300, 300])
+    fr = torch.from_numpy(frames).to(dev)
+    t0 = time.perf_counter()
+    geo = [PP.train_frame_geometry(jt_xyz[n], center_xyz[n], cube, img_size, O.NYU_PARAS, O.NYU_FLIP, augs[n]) for n in range(batch)]
+    host_ms = 1e3 * (time.perf_counter() - t0)
+    params = torch.from_numpy(np.stack([g[0] for g in geo])).to(dev)
+    out = torch.empty(batch, 1, img_size, img_size, device=dev)
+    call = lambda: L.check(L.lib().awr_crop_augment_normalize(L.ptr(fr), 0, batch, frames.shape[1], frames.shape[2], L.ptr(params), img_size, L.ptr(out),
+                                                              L.stream()), "awr_crop_augment_normalize")
+    for _ in range(3):
+        call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        call()
+    e1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / 20
+    return {"what": f"{batch} raw 480x640 float32 frames -> crop + random translate/scale/rotate (cv2-exact warps) + normalize, {img_size}x{img_size}",
+            "kernel_us_per_batch": round(us, 2), "kernel_frames_per_s": round(batch / (us * 1e-6), 0), "ctas": batch * 8,
+            "host_geometry_ms_per_batch": round(host_ms, 2), "host_frames_per_s_one_core": round(batch / (host_ms * 1e-3), 0),
+            "ops": {str(k): sum(1 for a_ in augs if a_[0] == k) for k in ("trans", "scale", "rot", None)}}
+
+
 def mean3d_diff_mm(uvd_ours, uvd_ref, B, J, img_size):
     """north_star's second bound: |mean 3-D error(ours) - mean 3-D error(reference)| in mm on the same synthetic batch, through the
     reference's UVD -> XYZ chain (util/eval_tool.py:34-49) with a synthetic NYU-like crop geometry and ground truth (checker role)."""
@@ -517,6 +553,12 @@ def main():
             parity["mean_3d_error_diff_mm_bf16"] = parity["headline_batch"]["mean_3d_error_diff_mm_bf16"]
         except Exception as e:
             parity["headline_batch"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    pre = None
+    if rank == 0 and world == 1 and not a.no_parity:
+        try:
+            pre = preprocess_leg(dev, a.batch, H)
+        except Exception as e:              # a reporting leg must never cost the bench line
+            pre = {"error": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0 and world == 1 and a.gpu_eager_baseline:
         eager = {"unit": UNIT, "what": "oracle's torch ops on this GPU (eager, cuDNN), same train step, device-resident batch"}
         for key, ac in (("fp32", False), ("bf16_autocast", True)):
@@ -542,6 +584,8 @@ def main():
             line["allreduce"] = allreduce
         if eager is not None:
             line["gpu_eager_baseline"] = eager
+        if pre is not None:
+            line["preprocess"] = pre
         print(json.dumps(line), flush=True)
     if world > 1:
         # the captured step graph holds NCCL kernels: release it, then leave without the communicator teardown (destroy_process_group can

@@ -188,3 +188,16 @@ def test_set_lr_and_optimizer_state_roundtrip():
     tr2.load_optimizer_state_dict(od)
     assert tr2.lr == 1e-4 and tr2.steps_done == 3 and tr2.step_dev.item() == 3.0
     assert torch.equal(tr2.m, tr.m) and torch.equal(tr2.v, tr.v)
+
+
+def test_unsupported_tensor_core_geometry_fails_with_a_named_layer():
+    """The tcgen05 path needs power-of-two feature maps (<= 256) and 64-channel multiples: a configuration outside that envelope is refused
+    at plan construction with the layer and the reason, and the same configuration runs in fp32 mode (CUDA-core kernels)."""
+    import awr_b200
+    from awr_b200.trainer import FusedTrainer
+    with pytest.raises(ValueError, match="power of two"):
+        FusedTrainer(awr_b200.get_deconv_net(18, 14, 2, precision="bf16").cuda(), 2, 96, 1.0, 1.0, 1.0)
+    tr = FusedTrainer(awr_b200.get_deconv_net(18, 14, 2, precision="fp32").cuda(), 2, 96, 1.0, 1.0, 1.0, use_graph=False)
+    img, jt = O.synthetic_batch(2, 96, 14, 3)
+    lc, ld = tr.train_step(img.cuda(), jt.cuda())
+    assert lc > 0 and ld > 0

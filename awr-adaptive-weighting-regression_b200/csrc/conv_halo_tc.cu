@@ -12,9 +12,10 @@
 // weight tile: per (tap, 64-channel block) ONE B tile feeds 8 MMAs (2 sub-tiles x K=64), halving weight traffic per FLOP.
 // Accumulators: 2 TMEM stages x 2 sub-tiles x Ntile (<=128) fp32 columns (exactly 4*Ntile columns are allocated).
 //
-// Round-2 structure (profiles/r02_halo_timeline.md: the round-1 kernel was bound by bytes in flight, not by the tensor pipe):
-//  * the producer is a two-queue state machine (halo patches / weight tiles) that polls both `empty` barriers and issues whichever
-//    TMA can go: halo patches run 2 k-steps ahead (3 halo stages where they fit) instead of waiting behind the weight ring;
+// Round-2 structure (profiles/r02_probes.md: the round-1 kernel was bound by bytes in flight, not by the tensor pipe):
+//  * halo patches and weight tiles have their own producer warps and rings (one thread issues one TMA per ~570 cycles whatever the box
+//    size, tools/dbg_tma_rate.py): halo patches run 2-3 k-steps ahead instead of waiting behind the weight ring, and weight tiles travel
+//    as pair stages (two taps per barrier round);
 //  * layers whose whole weight set fits (Cin = Cout = 64, 3x3: 72 KB) keep it RESIDENT in shared memory for the CTA's lifetime:
 //    per item only the 41 KB halo patch moves, and no weight-ring barrier traffic remains;
 //  * a CTA owns ONE output-channel tile for all its items, so the BatchNorm statistics live in registers across items: the
@@ -48,7 +49,7 @@ constexpr int kSmemBudget = 226 * 1024;       // dynamic shared memory incl. 1 K
 // so the A-window offset of a grid position, ((gy*(16+E) + gx) * 128 B, is a COMPILE-TIME constant: the MMA issue loop is straight-line
 // code whose descriptors differ by immediates.  (Round 1 looked the offsets up in a parameter table per tap: ~30 dependent R2UR / LDC
 // instructions in front of every 16 MMAs drained the tensor pipe's short queue -- 79 instead of 48 cycles per N=64 MMA,
-// profiles/r02_halo_timeline.md.)
+// profiles/r02_probes.md.)
 struct HaloClass {
   int mask, last_g, py, px, min_ox, min_oy, ntaps, pad_;
   short widx[9];
@@ -169,7 +170,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // The two operand streams have their own single-thread producers (this warp: one halo patch per (item, 64-channel block); warp 10: the
     // weight tiles), so the halo patches run halo_stages-1 k-steps ahead of the MMAs instead of queueing behind the weight ring, and neither
     // loop pays for the other's bookkeeping: a lone thread retires ~1 instruction per 5 cycles, so everything an issue needs is decoded once
-    // per item and the per-TMA path is poll / expect_tx / issue on 32-bit shared addresses (profiles/r02_halo_timeline.md).
+    // per item and the per-TMA path is poll / expect_tx / issue on 32-bit shared addresses (profiles/r02_probes.md).
     if (lane == 0) {
       const uint32_t hfull0 = smem_u32(&hfull[0]);
       int hs = 0; uint32_t hph = 0;
@@ -541,7 +542,7 @@ int conv_halo_launch(const ConvGeom& g, const void* in, const void* w, const flo
   // tuning overrides, read once (experiments only): AWR_HALO_STAGES = 2|3, AWR_HALO_RESIDENT = 0|1, AWR_HALO_NTILE = 64|128
   static const int env_hs = env_int("AWR_HALO_STAGES", 0), env_res = env_int("AWR_HALO_RESIDENT", 1), env_nt = env_int("AWR_HALO_NTILE", 0),
                    env_pair = env_int("AWR_HALO_PAIR", 0);       // CTA pairs + TMA multicast of the weight tiles: built, tested, NOT faster here
-                   // (profiles/r02_halo_timeline.md: L2 is not the limiter; 2.104 vs 2.088 ms per step), so off by default
+                   // (profiles/r02_probes.md: L2 is not the limiter; 2.104 vs 2.088 ms per step), so off by default
   HaloParams p;
   memset(&p, 0, sizeof(p));
   p.N = g.N; p.Hc = g.Hc; p.Wc = g.Wc; p.st_w = g.Wc / 16; p.st_h = g.Hc / 16; p.items_m = g.N * p.st_w * p.st_h;

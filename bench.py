@@ -29,6 +29,9 @@ J = 14
 H = 128
 
 
+CONV_TRAFFIC_PER_LAUNCH = 16158251      # bytes; ncu, headline config (see roofline.traffic_source)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -522,7 +525,11 @@ def main():
         ach = cfl / (cms * 1e-3) / 1e12
         roof = {"kernel": "tcgen05 conv/deconv implicit-GEMM kernels (conv_halo_kernel, conv_tc_kernel, wgrad_tc_kernel: fprop+dgrad+wgrad)",
                 "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sust"], 4),
-                "traffic": None, "peak_source": pk["src"] + " (sustained cuBLAS bf16 8192^3)", "launches_per_step": cn,
+                "traffic": CONV_TRAFFIC_PER_LAUNCH if (a.net == "resnet_18" and H == 128 and a.batch == 32) else None,
+                "traffic_source": "mean dram__bytes_read+write per launch over the 18 conv launches captured with ncu --set full "
+                                  "(profiles/r02_final_halo_full.md, r02_final_wgrad_full.md); the 64-channel 64x64 layers read their 16.9 MB "
+                                  "input once, writes stay in L2",
+                "peak_source": pk["src"] + " (sustained cuBLAS bf16 8192^3)", "launches_per_step": cn,
                 "avg_launch_us": round(1e3 * cms / cn, 2), "ms_per_step": round(cms, 4), "share_of_step": round(cms / (ms / a.steps), 4),
                 "flops_per_step": cfl, "how": "all conv launches of one step issued back to back between two CUDA events, 5 repetitions"}
         hv = [agg["head_fwd"], agg["head_bwd"]]

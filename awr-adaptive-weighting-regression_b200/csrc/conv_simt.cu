@@ -511,6 +511,9 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __res
   else if ((dtype) == AWR_DTYPE_BF16) { typedef bf16 T; __VA_ARGS__; }     \
   else return AWR_ERR_UNSUPPORTED;
 
+// csrc/stem_tc.cu
+int stem_conv_tc_launch(const float* x, const float* w, const float* bias, void* y, void* stats, int N, int H, int W, int Cout, int k, cudaStream_t st);
+
 extern "C" {
 
 int awr_conv_simt(const void* in, const float* w, const float* bias, void* out, int dtype, int N, int Hi, int Wi, int Ck, int Ho,
@@ -546,6 +549,12 @@ int awr_conv_wgrad_simt(const void* pointwise, const void* gathered, void* dW, i
 int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, void* stats, int dtype, int N, int H, int W, int Cout, int k,
                   void* stream) {
   AWR_HOST_CHECK(x && w && y && N > 0 && Cout % 8 == 0 && k % 2 == 1 && k <= 7);
+  // bf16 output, 64 channels, 5x5, rows that tile by 128 pixels: the tcgen05 kernel (csrc/stem_tc.cu).  AWR_STEM_TC=0 keeps the CUDA-core kernel.
+  static const bool stem_tc = [] { const char* e = getenv("AWR_STEM_TC"); return !(e && e[0] == '0'); }();
+  if (stem_tc && dtype == AWR_DTYPE_BF16) {
+    const int rc = stem_conv_tc_launch(x, w, bias, y, stats, N, H, W, Cout, k, (cudaStream_t)stream);
+    if (rc != AWR_ERR_UNSUPPORTED) return rc;
+  }
   if (k == 5 && W % 4 == 0 && (256 % (Cout / 8)) == 0 && (reinterpret_cast<unsigned long long>(x) & 15ull) == 0ull) {   // 16-byte patch loads
     const long long items4 = (long long)N * H * (W / 4) * (Cout / 8);
     long long blocks4 = (items4 + 255) / 256;

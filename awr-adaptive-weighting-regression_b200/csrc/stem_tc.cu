@@ -30,7 +30,7 @@ constexpr int kCout = 64;
 constexpr int kABytes = kTile * 128;             // 128 rows x 64 bf16
 constexpr int kBBytes = kCout * 128;             // 64 rows x 64 bf16
 constexpr int kPatchW = kTile + 4;               // 5 x 132 fp32 input patch
-constexpr int kSmemBytes = 2 * kABytes + 2 * kBBytes + 4 * 32 * 128 + 5 * kPatchW * 4 + 1024;
+constexpr int kSmemBytes = 2 * kABytes + 2 * kBBytes + 4 * 32 * 128 + 2 * 5 * kPatchW * 4 + 1024;
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -143,24 +143,43 @@ stem_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     __syncwarp();                                // the staging slice is free for the next tile
   };
 
+  // input patch of a tile: 5 x 132 fp32 (zero outside the image), element i = tid + 128 j; fetched into registers one tile ahead so
+  // that the global-load latency hides behind the A build and the epilogue of the tiles in flight
+  constexpr int kPatchPerThread = (5 * kPatchW + kStemThreads - 1) / kStemThreads;      // 6
+  int p_r[kPatchPerThread], p_c[kPatchPerThread];
+#pragma unroll
+  for (int j = 0; j < kPatchPerThread; ++j) { const int i = tid + j * kStemThreads; p_r[j] = i / kPatchW - 2; p_c[j] = i % kPatchW - 2; }
+  float pv[kPatchPerThread];
+  auto fetch_patch = [&](int tile) {
+    const int xb = tile % tpr; const int r2 = tile / tpr;
+    const int yy = r2 % H, n = r2 / H;
+    const float* xi = x + (size_t)n * H * W;
+#pragma unroll
+    for (int j = 0; j < kPatchPerThread; ++j) {
+      const int hh = yy + p_r[j], ww = xb * kTile + p_c[j];
+      pv[j] = (hh >= 0 && hh < H && ww >= 0 && ww < W && p_r[j] < 3) ? __ldg(xi + (size_t)hh * W + ww) : 0.f;
+    }
+  };
+  auto store_patch = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < kPatchPerThread; ++j) {
+      const int i = tid + j * kStemThreads;
+      if (i < 5 * kPatchW) sPatch[buf * 5 * kPatchW + i] = pv[j];
+    }
+  };
   int it = 0, prev_tile = -1;
+  if ((int)blockIdx.x < total) { fetch_patch(blockIdx.x); store_patch(0); }
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
     const int s = it & 1;
-    const int xb = tile % tpr; int r2 = tile / tpr;
-    const int yy = r2 % H, n = r2 / H;
-    // ---- 5 x 132 input patch (zero outside the image) ----------------------------------------------------------------------------
-    const float* xi = x + (size_t)n * H * W;
-    for (int i = tid; i < 5 * kPatchW; i += kStemThreads) {
-      const int pr = i / kPatchW, pc = i - pr * kPatchW;
-      const int hh = yy + pr - 2, ww = xb * kTile + pc - 2;
-      sPatch[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + (size_t)hh * W + ww) : 0.f;
-    }
-    __syncthreads();                             // (also: every warp has finished the previous iteration's epilogue reads of TMEM stage s^1 ... see below)
+    __syncthreads();                             // patch buffer s is complete; every warp is past the previous iteration's epilogue
+    const int next = tile + gridDim.x;
+    if (next < total) fetch_patch(next);
     // ---- im2col row of pixel `tid`: hi | lo, K-major, swizzled ---------------------------------------------------------------------
     {
+      const float* pt = sPatch + s * 5 * kPatchW;
       float tv[32];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) tv[t] = t < 25 ? sPatch[(t / 5) * kPatchW + tid + (t % 5)] : 0.f;
+      for (int t = 0; t < 32; ++t) tv[t] = t < 25 ? pt[(t / 5) * kPatchW + tid + (t % 5)] : 0.f;
       uint8_t* arow = sA + s * kABytes + tid * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -193,9 +212,10 @@ stem_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     }
     __syncwarp();
     // ---- while those run: drain the previous tile (stage s^1).  Its A stage and TMEM stage are reused at iteration it+1, after the
-    //      __syncthreads above, i.e. after every warp has finished this epilogue.
+    //      __syncthreads at the top of the loop, i.e. after every warp has finished this epilogue.
     if (prev_tile >= 0) epilogue(prev_tile, s ^ 1, (uint32_t)(((it - 1) >> 1) & 1));
     prev_tile = tile;
+    if (next < total) store_patch(s ^ 1);        // buffer s^1 was last read before this iteration's second __syncthreads
   }
   if (prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1, (uint32_t)(((it - 1) >> 1) & 1));
 

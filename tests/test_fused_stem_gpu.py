@@ -114,3 +114,31 @@ def test_bn_relu_maxpool3_fwd_bf16_value_and_argmax():
     first_c = (p - wo * s).clamp_min(0)
     first = (first_r * k + first_c).expand_as(tap)
     assert zero.any() and (tap[zero] == first[zero]).all()
+
+
+@pytest.mark.parametrize("N,H,W,with_bias", [(3, 8, 128, True), (2, 16, 256, False), (5, 128, 128, False)])
+def test_stem_conv_tensor_core_bf16(N, H, W, with_bias):
+    """csrc/stem_tc.cu: the 1-channel 5x5 stem on tcgen05 with a hand-built im2col operand (hi/lo bf16 split of the fp32 depth and of the
+    weights).  The bf16 output equals torch's fp32 convolution to output rounding (one bf16 ulp = 2^-8 relative), far tighter than a plain
+    bf16 x bf16 product would be; the fused statistics are the sums of the stored values."""
+    from awr_b200 import _lib as L
+    Co, k = 64, 5
+    g = torch.Generator().manual_seed(N * 1000 + W)
+    x = torch.randn(N, 1, H, W, generator=g).cuda()
+    x[:, :, :, :3] = 1.0                                                      # background columns at the left border
+    w = (torch.randn(Co, 1, k, k, generator=g) * 0.2).cuda()
+    b = torch.randn(Co, generator=g).cuda() if with_bias else None
+    ref = F.conv2d(x, w, b, padding=2)
+    y = torch.full((N, H, W, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = L.acc_zeros(2 * Co, "cuda")
+    w_phys = w.permute(2, 3, 0, 1).contiguous().view(k * k, Co)
+    L.check(L.lib().awr_stem_conv(x.data_ptr(), w_phys.data_ptr(), None if b is None else b.data_ptr(), y.data_ptr(), stats.data_ptr(), L.BF16,
+                                  N, H, W, Co, k, L.stream()), "stem")
+    torch.cuda.synchronize()
+    got = y.float().permute(0, 3, 1, 2)
+    assert not torch.isnan(got).any()
+    err = (got - ref).abs()
+    assert (err <= ref.abs() * 2.0 ** -8 + 2e-5).all(), (err.max().item(), (err / (ref.abs() + 1e-3)).max().item())
+    st = L.acc_to_float(stats).double()
+    assert torch.allclose(st[:Co], got.double().sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[Co:], (got.double() ** 2).sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)

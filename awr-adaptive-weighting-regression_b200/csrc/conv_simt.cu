@@ -513,6 +513,7 @@ __global__ void __launch_bounds__(256) stem_conv_tiled_kernel(const float* __res
 
 // csrc/stem_tc.cu
 int stem_conv_tc_launch(const float* x, const float* w, const float* bias, void* y, void* stats, int N, int H, int W, int Cout, int k, cudaStream_t st);
+int stem_wgrad_tc_launch(const float* x, const void* dy, void* dW, void* dbias, int N, int H, int W, int Cout, int k, cudaStream_t st);
 
 extern "C" {
 
@@ -578,6 +579,11 @@ int awr_stem_conv(const float* x, const float* w, const float* bias, void* y, vo
 int awr_stem_wgrad(const float* x, const void* dy, void* dW, void* dbias, int dtype, int N, int H, int W, int Cout, int k,
                    void* stream) {
   AWR_HOST_CHECK(x && dy && dW && N > 0 && (Cout == 64 || Cout == 128 || Cout == 256) && k % 2 == 1 && k <= 7);
+  static const bool stem_tc = [] { const char* e = getenv("AWR_STEM_TC"); return !(e && e[0] == '0'); }();
+  if (stem_tc && dtype == AWR_DTYPE_BF16) {
+    const int rc = stem_wgrad_tc_launch(x, dy, dW, dbias, N, H, W, Cout, k, (cudaStream_t)stream);
+    if (rc != AWR_ERR_UNSUPPORTED) return rc;
+  }
   const long long P = (long long)N * H * W;
   const int ppb = 256;
   AWR_HOST_CHECK((k * k + (256 / Cout) - 1) / (256 / Cout) <= 8 * 1 || true);

@@ -243,6 +243,162 @@ stem_conv_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 128); }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the stem on tcgen05:  dW[tap][c] = sum over pixels of patch[pixel][tap] * dy[pixel][c]  (+ dbias[c] = sum of dy).
+// The contraction runs over PIXELS, so both operands are MN-major: the hand-built im2col tile [pixel][hi | lo taps] of the forward kernel,
+// read through an MN-major descriptor, is A^T (M = 64 tap rows, padded to M = 128 by a second, all-zero 64-row atom reached through the
+// descriptor's leading-dimension offset), and dy's NHWC tile [pixel][64 channels] arrives by TMA as B.  A constant 1.0 in tap slot 25 makes
+// row 25 of D the bias gradient.  One accumulator D[128 x 64] in TMEM per CTA for its whole pixel range; the epilogue adds the hi and lo
+// rows of each tap and issues one atomic per (tap, channel) and CTA.
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int kWgSmemBytes = 2 * kABytes + kABytes + 2 * kABytes + 2 * 5 * kPatchW * 4 + 1024;      // A x2, zero atom, dy x2, patches
+
+__global__ void __launch_bounds__(kStemThreads, 2)
+stem_wgrad_tc_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tmDy, GradT* __restrict__ dW, GradT* __restrict__ dbias,
+                     int N, int H, int W) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
+  __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* base = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  uint8_t* sA = base;                            // 2 stages x [128 pixels][hi | lo taps]
+  uint8_t* sZ = base + 2 * kABytes;              // the all-zero second M atom
+  uint8_t* sDy = sZ + kABytes;                   // 2 stages x [128 pixels][64 channels] (TMA, SWIZZLE_128B)
+  float* sPatch = reinterpret_cast<float*>(sDy + 2 * kABytes);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmDy);
+    for (int i = 0; i < 2; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < kABytes / 16; i += kStemThreads) reinterpret_cast<uint4*>(sZ)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();
+
+  const int tpr = W / kTile;
+  const int total = N * H * tpr;
+  // contiguous tile range per CTA
+  const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t0 = (int)blockIdx.x * per, t1 = min(total, t0 + per);
+  const uint32_t idesc = umma_idesc_bf16(128, kCout, 1, 1);
+
+  constexpr int kPatchPerThread = (5 * kPatchW + kStemThreads - 1) / kStemThreads;
+  int p_r[kPatchPerThread], p_c[kPatchPerThread];
+#pragma unroll
+  for (int j = 0; j < kPatchPerThread; ++j) { const int i = tid + j * kStemThreads; p_r[j] = i / kPatchW - 2; p_c[j] = i % kPatchW - 2; }
+  float pv[kPatchPerThread];
+  auto fetch_patch = [&](int tile) {
+    const int xb = tile % tpr; const int r2 = tile / tpr;
+    const int yy = r2 % H, n = r2 / H;
+    const float* xi = x + (size_t)n * H * W;
+#pragma unroll
+    for (int j = 0; j < kPatchPerThread; ++j) {
+      const int hh = yy + p_r[j], ww = xb * kTile + p_c[j];
+      pv[j] = (hh >= 0 && hh < H && ww >= 0 && ww < W && p_r[j] < 3) ? __ldg(xi + (size_t)hh * W + ww) : 0.f;
+    }
+  };
+  auto store_patch = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < kPatchPerThread; ++j) {
+      const int i = tid + j * kStemThreads;
+      if (i < 5 * kPatchW) sPatch[buf * 5 * kPatchW + i] = pv[j];
+    }
+  };
+
+  if (t0 < t1) {
+    fetch_patch(t0); store_patch(0);
+    if (tid == 0) {
+      mbar_expect_tx(&full_bar[0], (uint32_t)kABytes);
+      tma_load_3d(sDy, &tmDy, &full_bar[0], 0, 0, t0);
+    }
+  }
+  int it = 0;
+  for (int tile = t0; tile < t1; ++tile, ++it) {
+    const int s = it & 1;
+    if (it >= 2) mbar_wait(&empty_bar[s], (uint32_t)(((it >> 1) - 1) & 1));    // the MMAs that read A[s] / dy[s] two tiles ago are done
+    __syncthreads();                             // patch buffer s complete
+    const int next = tile + 1;
+    if (next < t1) fetch_patch(next);
+    {
+      const float* pt = sPatch + s * 5 * kPatchW;
+      float tv[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) tv[t] = t < 25 ? pt[(t / 5) * kPatchW + tid + (t % 5)] : (t == 25 ? 1.f : 0.f);       // slot 25: the bias row
+      uint8_t* arow = sA + s * kABytes + tid * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = tv[8 * j + 2 * q], b = tv[8 * j + 2 * q + 1];
+          const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+          hi[q] = pack_bf16(a, b);
+          lo[q] = pack_bf16(a - ah, b - bh);
+        }
+        *reinterpret_cast<uint4*>(arow + ((j ^ (tid & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(arow + (((4 + j) ^ (tid & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_wait(&full_bar[s], (uint32_t)((it >> 1) & 1));            // dy tile landed
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA) + s * kABytes;
+        const uint32_t lbo = (smem_u32(sZ)) - a0;                       // second M atom: the zero block
+        const uint64_t ad = umma_desc_sw128(a0, lbo, 1024);
+        const uint64_t bd = umma_desc_sw128(smem_u32(sDy) + s * kABytes, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(tmem_base, ad + (uint64_t)(k * 128), bd + (uint64_t)(k * 128), idesc, (it | k) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (next < t1) {                                                // dy of the next tile into the other stage (its last readers: tile it-1)
+          if (it >= 1) mbar_wait(&empty_bar[s ^ 1], (uint32_t)((((it - 1) >> 1)) & 1));
+          mbar_expect_tx(&full_bar[s ^ 1], (uint32_t)kABytes);
+          tma_load_3d(sDy + (s ^ 1) * kABytes, &tmDy, &full_bar[s ^ 1], 0, 0, next);
+        }
+      }
+      __syncwarp();
+    }
+    if (next < t1) store_patch(s ^ 1);
+  }
+  if (warp == 0 && elect_one()) {
+    if (it > 0) umma_commit(&done_bar); else mbar_arrive(&done_bar);
+  }
+  __syncwarp();
+  mbar_wait(&done_bar, 0u);
+  tc_fence_after();
+
+  // ---- epilogue: D rows 0..25 (hi taps, bias row) sit in warp 0's TMEM lanes, rows 32..56 (lo taps) in warp 1's -------------------------
+  float* sHi = reinterpret_cast<float*>(sA);     // [32][64] fp32 each (the operand stages are idle now)
+  float* sLo = sHi + 32 * 64;
+  if (warp < 2 && it > 0) {
+    uint32_t v0[32], v1[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    tmem_ld32(taddr, v0);
+    tmem_ld32(taddr + 32, v1);
+    tmem_ld_wait();
+    float* dst = (warp == 0 ? sHi : sLo) + (tid & 31) * 64;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { dst[c] = __uint_as_float(v0[c]); dst[32 + c] = __uint_as_float(v1[c]); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (it > 0) {
+    for (int i = tid; i < 25 * kCout; i += kStemThreads) grad_add(dW + i, sHi[i] + sLo[i]);
+    if (dbias && tid < kCout) grad_add(dbias + tid, sHi[25 * kCout + tid] + sLo[25 * kCout + tid]);
+  }
+  if (warp == 0) { __syncwarp(); tmem_dealloc(tmem_base, 64); }
+}
+
 }  // namespace
 
 // bf16 NHWC output, Cout = 64, k = 5, W a multiple of 128.  Returns AWR_ERR_UNSUPPORTED otherwise (the caller falls back to the CUDA-core kernel).
@@ -255,6 +411,29 @@ int stem_conv_tc_launch(const float* x, const float* w, const float* bias, void*
   const int total = N * H * (W / kTile);
   const int grid = total < 3 * awr_sm_budget() ? total : 3 * awr_sm_budget();
   launch_pdl(stem_conv_tc_kernel, dim3(grid), dim3(kStemThreads), (size_t)kSmemBytes, st, x, w, bias, (__nv_bfloat16*)y, (AwrAcc*)stats, N, H, W);
+  AWR_LAUNCH_CHECK();
+  return AWR_OK;
+}
+
+// dy bf16 NHWC (N,H,W,64), k = 5, W a multiple of 128; dW [25][64] and dbias [64] (optional) are accumulated into (GradT: fp32, or the
+// accumulator slots of the bit-reproducible build).  Returns AWR_ERR_UNSUPPORTED for other shapes.
+int stem_wgrad_tc_launch(const float* x, const void* dy, void* dW, void* dbias, int N, int H, int W, int Cout, int k, cudaStream_t st) {
+  if (!(Cout == kCout && k == 5 && W % kTile == 0 && N > 0 && H > 0)) return AWR_ERR_UNSUPPORTED;
+  static const bool configured = [] {
+    return cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes) == cudaSuccess;
+  }();
+  if (!configured) return AWR_ERR_DRIVER;
+  const int total = N * H * (W / kTile);
+  CUtensorMap tm;
+  {
+    const long long dims[3] = {kCout, kTile, total};
+    const long long str[3] = {1, kCout, (long long)kTile * kCout};
+    const int box[3] = {kCout, kTile, 1};
+    if (!make_tmap_bf16(&tm, dy, 3, dims, str, box, nullptr)) return AWR_ERR_DRIVER;
+  }
+  const int grid = total < 2 * awr_sm_budget() ? total : 2 * awr_sm_budget();
+  launch_pdl(stem_wgrad_tc_kernel, dim3(grid), dim3(kStemThreads), (size_t)kWgSmemBytes, st, x, tm, reinterpret_cast<GradT*>(dW),
+             reinterpret_cast<GradT*>(dbias), N, H, W);
   AWR_LAUNCH_CHECK();
   return AWR_OK;
 }

@@ -142,3 +142,33 @@ def test_stem_conv_tensor_core_bf16(N, H, W, with_bias):
     st = L.acc_to_float(stats).double()
     assert torch.allclose(st[:Co], got.double().sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(st[Co:], (got.double() ** 2).sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("N,H,W,with_bias", [(3, 8, 128, True), (2, 16, 256, False), (5, 128, 128, True)])
+def test_stem_wgrad_tensor_core_bf16(N, H, W, with_bias):
+    """csrc/stem_tc.cu: stem weight gradient as a pixel-contraction GEMM on tcgen05 (MN-major hand-built im2col operand x TMA-loaded dy; the
+    bias gradient rides along as a constant-one tap).  dy is bf16, the depth keeps fp32 accuracy through the hi/lo split, accumulation is
+    fp32: the result matches torch's fp32 weight gradient on the same bf16 dy to accumulation-order error."""
+    from awr_b200 import _lib as L
+    Co, k = 64, 5
+    g = torch.Generator().manual_seed(N * 100 + W)
+    x = torch.randn(N, 1, H, W, generator=g).cuda()
+    dy = torch.randn(N, Co, H, W, generator=g).bfloat16().cuda()
+    w = torch.zeros(Co, 1, k, k, device="cuda", dtype=torch.float64, requires_grad=True)      # float64 reference (no TF32, no ordering noise)
+    b = torch.zeros(Co, device="cuda", dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, b, padding=2).backward(dy.double())
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    det = L.deterministic()
+    dW = L.acc_zeros(k * k * Co, "cuda") if det else torch.zeros(k * k, Co, device="cuda")
+    db = (L.acc_zeros(Co, "cuda") if det else torch.zeros(Co, device="cuda")) if with_bias else None
+    L.check(L.lib().awr_stem_wgrad(x.data_ptr(), dyn.data_ptr(), dW.data_ptr(), None if db is None else db.data_ptr(), L.BF16, N, H, W, Co, k,
+                                   L.stream()), "stem_wgrad")
+    torch.cuda.synchronize()
+    got = (L.acc_to_float(dW) if det else dW).float().view(k, k, Co).permute(2, 0, 1)
+    ref = w.grad[:, 0]
+    err = (got.double() - ref).abs().max().item()
+    print(f"stem wgrad N={N} {H}x{W}: max |dW - float64 reference| = {err:.3e} of {ref.abs().max().item():.1f}")
+    assert err < 2e-5 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+    if with_bias:
+        gb = (L.acc_to_float(db) if det else db).double()
+        assert (gb - b.grad).abs().max().item() < 2e-5 * b.grad.abs().max().item() + 1e-3

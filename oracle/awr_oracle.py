@@ -1,7 +1,7 @@
 """CPU oracle for the AWR dense hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT.
 
 Only tests/ (+ tests/golden/make_*.py), __graft_entry__.smoke(), bench.py's cpu_baseline /
---impl reference / parity / --gpu-eager-baseline legs and the developer scripts under tools/
+--impl reference / parity / gpu_eager_baseline / preprocess legs and the developer scripts under tools/
 import this file, always as the checker, the timed CPU baseline or a seeded input generator.
 The product path (awr_b200) never does -- tests/test_abi.py greps the package for it -- and
 fails loudly when the CUDA library is missing.

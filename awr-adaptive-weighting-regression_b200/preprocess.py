@@ -210,6 +210,132 @@ def train_frame_geometry(jt_xyz, center_xyz, cube, img_size, paras, flip, aug):
             cube.astype(np.float32))
 
 
+def _bounds_batch(center, csize, paras):
+    """center2bounds for N frames: center (N,3) float32, csize (N,3) float64.  Same float64 expressions, element by element."""
+    p2 = np.asarray(paras[:2])
+    half = (csize[:, :2] / 2.) / center[:, 2:3] * p2
+    lo, hi = center[:, :2] - half + 0.5, center[:, :2] + half + 0.5
+    z = center[:, 2].astype(np.float64)
+    return (np.trunc(lo[:, 0]).astype(np.int64), np.trunc(hi[:, 0]).astype(np.int64), np.trunc(lo[:, 1]).astype(np.int64),
+            np.trunc(hi[:, 1]).astype(np.int64), z - csize[:, 2] / 2., z + csize[:, 2] / 2.)
+
+
+def _transmat_batch(ustart, uend, vstart, vend, D):
+    """center2transmat for N frames from their bounds, in closed form: trans2 . diag(sc, sc, 1) . trans1 has one rounded product and one
+    addition per translation entry, which is what the 3x3 float64 matrix products of the reference evaluate to.  Returns
+    (M (N,3,3) float32, sc, size_w, size_h, t2x, t2y)."""
+    w, h = uend - ustart, vend - vstart
+    sc = np.minimum(D / w, D / h)
+    sw, sh = np.trunc(w * sc).astype(np.int64), np.trunc(h * sc).astype(np.int64)
+    t2x, t2y = np.floor(D / 2. - sw / 2.).astype(np.int64), np.floor(D / 2. - sh / 2.).astype(np.int64)
+    M = np.zeros((len(w), 3, 3), np.float64)
+    M[:, 0, 0] = sc; M[:, 1, 1] = sc; M[:, 2, 2] = 1.0
+    M[:, 0, 2] = sc * (-ustart) + t2x
+    M[:, 1, 2] = sc * (-vstart) + t2y
+    return M.astype(np.float32), sc, sw, sh, t2x, t2y
+
+
+def train_batch_geometry(jt_xyz, center_xyz, cube, img_size, paras, flip, augs):
+    """train_frame_geometry for a whole batch: the same float32 / float64 expressions evaluated on arrays with a leading frame axis (grouped
+    by augmentation, because the rotate branch continues in float32 where the others stay in float64), with only the calls whose rounding
+    depends on the library routine left per frame (the float32 LAPACK inverse and 3x3 products, libm cos / sin).  Bit-identical to the
+    per-frame function (tests/test_augment.py); ~10x faster.  Returns (rows (N,32) f64, jt_xyz_norm (N,J,3), jt_uvd_norm (N,J,3),
+    center_xyz (N,3), M (N,3,3), cube (N,3)), float32 labels."""
+    N = len(augs)
+    D = int(img_size)
+    jt_xyz, center_xyz = np.asarray(jt_xyz, dtype=np.float64), np.asarray(center_xyz, dtype=np.float64)
+    J = jt_xyz.shape[1]
+    cube0 = np.asarray(cube)
+    csize = np.broadcast_to(np.asarray(cube0, dtype=np.float64), (N, 3)).copy()              # per frame; scaled below
+    center = xyz2uvd(center_xyz, paras, flip)                                                 # (N,3) float32
+    jt64 = jt_xyz - center_xyz[:, None, :]
+    rows = np.zeros((N, 32), np.float64)
+    us, ue, vs, ve, zs, ze = _bounds_batch(center, csize, paras)
+    if np.any(ue - us <= 0) or np.any(ve - vs <= 0):
+        n = int(np.argmax((ue - us <= 0) | (ve - vs <= 0)))
+        raise ValueError(f"frame {n}: empty crop box (centre depth {center[n][2]})")
+    M, sc, sw, sh, t2x, t2y = _transmat_batch(us, ue, vs, ve, D)
+    rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], rows[:, 5] = us, vs, ue - us, ve - vs, sw, sh
+    rows[:, 6], rows[:, 7] = np.trunc((D - sw) / 2.), np.trunc((D - sh) / 2.)
+    rows[:, 8], rows[:, 9] = zs, ze
+    ops = [a[0] for a in augs]
+    trans = np.stack([np.asarray(a[1], dtype=np.float64) for a in augs])
+    scale = np.array([float(a[2]) for a in augs])
+    is_trans = np.array([o == "trans" for o in ops]) & ~np.all(np.isclose(trans, 0.), axis=1)
+    is_rot = np.array([o == "rot" for o in ops])
+    is_scale = np.array([o == "scale" for o in ops]) & ~np.isclose(scale, 1.)
+    new_M = M.copy()
+    warp = np.zeros(N, bool)                                                                  # frames that go through Loader.recrop
+
+    # ---- translate (loader.py:103-123) ------------------------------------------------------------------------------------------------
+    if is_trans.any():
+        i = np.nonzero(is_trans)[0]
+        c_old = center[i]
+        c_new = xyz2uvd(uvd2xyz(c_old, paras, flip) + trans[i], paras, flip)
+        redo = ~np.isclose(c_old[:, 2], 0.) | np.isclose(c_new[:, 2], 0.)
+        b = _bounds_batch(c_new, csize[i], paras)
+        Mn = _transmat_batch(b[0], b[1], b[2], b[3], D)[0]
+        new_M[i[redo]] = Mn[redo]
+        warp[i[redo]] = True
+        rows[i[redo], 22], rows[i[redo], 23] = b[4][redo], b[5][redo]
+        jt64[i] = jt64[i] + uvd2xyz(c_old, paras, flip)[:, None, :] - uvd2xyz(c_new, paras, flip)[:, None, :]
+        center[i] = c_new
+    # ---- scale (loader.py:163-179) ------------------------------------------------------------------------------------------------------
+    if is_scale.any():
+        i = np.nonzero(is_scale)[0]
+        csize[i] = cube0 * scale[i][:, None]
+        redo = ~np.isclose(center[i][:, 2], 0.)
+        b = _bounds_batch(center[i], csize[i], paras)
+        Mn = _transmat_batch(b[0], b[1], b[2], b[3], D)[0]
+        new_M[i[redo]] = Mn[redo]
+        warp[i[redo]] = True
+        rows[i[redo], 22], rows[i[redo], 23] = b[4][redo], b[5][redo]
+    if warp.any():
+        inv = np.linalg.inv(M[warp])                                                          # float32 LAPACK inverse per matrix, as the reference calls it
+        for k, n in enumerate(np.nonzero(warp)[0]):
+            rows[n, 12] = 1
+            rows[n, 13:22] = invert3x3(np.dot(new_M[n], inv[k]))
+    M = new_M
+    # ---- rotate (loader.py:141-161): continues in float32 -------------------------------------------------------------------------------
+    jt32 = None
+    if is_rot.any():
+        i = np.nonzero(is_rot)[0]
+        r = [np.mod(augs[n][3], 360) for n in i]
+        rows[i, 12] = 2
+        for k, n in enumerate(i):
+            rows[n, 13:19] = rotation_inverse_map((D, D), -r[k])
+        alpha = [rk * np.pi / 180. for rk in r]
+        ca, sa = np.array([np.cos(a) for a in alpha])[:, None], np.array([np.sin(a) for a in alpha])[:, None]
+        c = center[i]
+        c_xyz = uvd2xyz(c, paras, flip)
+        pt = xyz2uvd(jt64[i] + c_xyz[:, None, :], paras, flip)                                # (n,J,3) float32
+        rot = pt.copy()
+        dx, dy = pt[:, :, 0] - c[:, 0:1], pt[:, :, 1] - c[:, 1:2]
+        rot[:, :, 0] = dx * ca - dy * sa
+        rot[:, :, 1] = dx * sa + dy * ca
+        rot[:, :, :2] += c[:, None, :2]
+        jt32 = uvd2xyz(rot.astype(np.float32), paras, flip) - c_xyz[:, None, :]             # float32 from here on
+    rows[:, 24] = _perspective_tile_width(D)
+    rows[:, 10], rows[:, 11] = center[:, 2], csize[:, 2] / 2.
+    # ---- labels (nyu_loader.py:58-66) ---------------------------------------------------------------------------------------------------
+    c_xyz = uvd2xyz(center, paras, flip)
+    q = np.empty((N, J, 3), np.float32)
+    jt_n = np.empty((N, J, 3), np.float32)
+    f64 = ~is_rot
+    q[f64] = xyz2uvd(jt64[f64] + c_xyz[f64][:, None, :], paras, flip)
+    jt_n[f64] = (jt64[f64] / (csize[f64] / 2.)[:, None, :]).astype(np.float32)
+    if jt32 is not None:
+        q[is_rot] = xyz2uvd(jt32 + c_xyz[is_rot][:, None, :], paras, flip)
+        jt_n[is_rot] = (jt32 / (csize[is_rot] / 2.)[:, None, :]).astype(np.float32)
+    pts = np.concatenate([q[:, :, :2], np.ones((N, J, 1))], axis=2)                           # (N,J,3) float64, as the reference's hstack
+    hom = np.stack([np.dot(M[n], pts[n].T).T for n in range(N)])                              # float32 x float64 3x3 products: per frame, as the reference
+    hom[:, :, :2] /= hom[:, :, 2:]
+    jt_uvd = np.concatenate([hom[:, :, :2], q[:, :, 2:]], axis=2).astype(np.float32)
+    jt_uvd[:, :, :2] = jt_uvd[:, :, :2] / (D / 2.) - 1
+    jt_uvd[:, :, 2] = (jt_uvd[:, :, 2] - c_xyz[:, 2:3]) / (csize[:, 2:3] / 2.0)
+    return rows, jt_n, jt_uvd, c_xyz.astype(np.float32), M.astype(np.float32), csize.astype(np.float32)
+
+
 def train_batch(frames, jt_xyz, center_xyz, cube, img_size, paras, flip, augs):
     """The reference's training items for a batch of raw frames (what collating NYU.__getitem__ over N indices returns), pixels on the GPU.
     frames: CUDA (N,Hs,Ws) float32 mm or (N,Hs,Ws,3) uint8 BGR; jt_xyz (N,J,3) / center_xyz (N,3) float64 mm as nyu_loader.make_dataset holds
@@ -226,9 +352,9 @@ def train_batch(frames, jt_xyz, center_xyz, cube, img_size, paras, flip, augs):
     N, Hs, Ws = frames.shape[:3]
     if len(augs) != N:
         raise ValueError("one augmentation draw per frame")
-    geo = [train_frame_geometry(jt_xyz[n], center_xyz[n], cube, img_size, paras, flip, augs[n]) for n in range(N)]
-    params = torch.from_numpy(np.stack([g[0] for g in geo])).to(frames.device)
+    geo = train_batch_geometry(jt_xyz, center_xyz, cube, img_size, paras, flip, augs)
+    params = torch.from_numpy(geo[0]).to(frames.device)
     out = torch.empty(N, 1, img_size, img_size, dtype=torch.float32, device=frames.device)
     L.check(L.lib().awr_crop_augment_normalize(L.ptr(frames), fmt, N, Hs, Ws, L.ptr(params), int(img_size), L.ptr(out), L.stream()),
             "awr_crop_augment_normalize")
-    return (out,) + tuple(torch.from_numpy(np.stack([g[k] for g in geo])) for k in range(1, 6))
+    return (out,) + tuple(torch.from_numpy(np.ascontiguousarray(g)) for g in geo[1:])

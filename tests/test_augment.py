@@ -46,6 +46,27 @@ def test_random_stream_and_host_geometry_match_reference(i, N, seed, D):
         assert row.shape == (32,) and row[12] == {"trans": 1, "scale": 1, "rot": 2, None: 0}[op]
 
 
+@pytest.mark.parametrize("i,N,seed,D", CASES, ids=lambda v: str(v))
+def test_batched_host_geometry_is_bit_identical(i, N, seed, D):
+    """preprocess.train_batch_geometry (array form, what train_batch uses) against the per-frame function and the reference's labels; plus a
+    random stream of 64 further draws per case."""
+    from awr_b200 import preprocess as PP
+    frames, jt_xyz, center_xyz = O.augment_case_inputs(N, seed)
+    bat = PP.train_batch_geometry(jt_xyz, center_xyz, CUBE, D, O.NYU_PARAS, O.NYU_FLIP, _augs(i, N))
+    for o, k in zip(bat[1:], KEYS[1:]):
+        assert o.dtype == np.float32 and np.array_equal(o, G[f"{k}{i}"]), k
+    rs = np.random.RandomState(seed)
+    _, jt2, c2 = O.augment_case_inputs(64, seed + 50)
+    augs = [PP.random_aug(rs, *G[f"aug_para{i}"]) for _ in range(64)]
+    augs[3] = ("trans", np.zeros(3), 1.0, 0.0)                           # the early-return branches (loader.py:109-110,167-168)
+    augs[4] = ("scale", np.zeros(3), 1.0, 0.0)
+    per = [PP.train_frame_geometry(jt2[n], c2[n], CUBE, D, O.NYU_PARAS, O.NYU_FLIP, augs[n]) for n in range(64)]
+    bat = PP.train_batch_geometry(jt2, c2, CUBE, D, O.NYU_PARAS, O.NYU_FLIP, augs)
+    for k in range(6):
+        a = np.stack([p[k] for p in per])
+        assert a.dtype == bat[k].dtype and np.array_equal(a, bat[k]), k
+
+
 def test_matrix_helpers_match_cv2():
     cv2 = pytest.importorskip("cv2")
     from awr_b200 import preprocess as PP

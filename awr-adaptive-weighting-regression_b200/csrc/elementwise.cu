@@ -35,6 +35,18 @@ inline int ew_grid(long long items, int U) {
   if (b > 148 * 4) b = 148 * 4;
   return (int)b;
 }
+// whole waves: a grid-stride kernel whose CTAs do not all fit at once runs its last, partial wave at a fraction of the machine (ncu, round 2:
+// bn_relu_maxpool3_fwd at 80 registers fits 3 CTAs per SM, so the 592-CTA cap above was 1.33 waves).  Cap the grid at the resident CTA count.
+template <auto Kernel>
+inline int wave_grid(long long needed) {
+  static const int occ = [] {
+    int o = 0;
+    return (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, Kernel, kEwThreads, 0) == cudaSuccess && o > 0) ? o : 2;
+  }();
+  const long long cap = (long long)awr_sm_budget() * occ;
+  if (needed < 1) needed = 1;
+  return (int)(needed < cap ? needed : cap);
+}
 // 16-byte loads in flight per thread and tensor of the BatchNorm passes: two register batches of U/2 items (AWR_EW_UNROLL=2|4; default 4)
 inline int ew_unroll() {
   static const int u = [] { const char* e = getenv("AWR_EW_UNROLL"); const int v = e ? atoi(e) : 4; return (v == 1 || v == 2) ? v : 4; }();
@@ -1508,7 +1520,7 @@ int awr_bn_relu_maxpool_fwd(const void* y, const void* sums, const float* gamma,
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
   BnSet a{(const AwrAcc*)sums, gamma, beta, running_mean, running_var, num_batches_tracked, mean_invstd};
   if (k == 3 && ew_unroll() > 1) {
-    DISPATCH_T(dtype, launch_pdl(bn_relu_maxpool3_fwd_kernel<T>, dim3(ew_grid((long long)N * Ho * Wo * (C / 8), 1)), dim3(kEwThreads), 0, (cudaStream_t)stream,
+    DISPATCH_T(dtype, launch_pdl(bn_relu_maxpool3_fwd_kernel<T>, dim3(wave_grid<bn_relu_maxpool3_fwd_kernel<T>>(((long long)N * Ho * Wo * (C / 8) + kEwThreads - 1) / kEwThreads)), dim3(kEwThreads), 0, (cudaStream_t)stream,
                           (const T*)y, a, (T*)out, idx, N, H, W, C, Ho, Wo, s, p, (float)((long long)N * H * W), momentum, eps, training));
     AWR_LAUNCH_CHECK();
     return AWR_OK;

@@ -642,7 +642,8 @@ class _Conv(_Op):
                 pl.call(pl.bwd, "awr_conv_wgrad_tc", x.t, dy, gW, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k, self.stride,
                         self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
             if self.bname:
-                pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.arena(ACC * self.Cout), 0, pl.G(self.bname), pl.arena(1))
+                pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.arena(ACC * self.Cout), 0, pl.G(self.bname), pl.arena(1),
+                        side=True)          # bias gradient: like the weight gradient, nothing downstream in backward consumes it
             w16 = pl.W16(self.wname)
 
             def emit_tc(dst, acc):
@@ -658,7 +659,8 @@ class _Conv(_Op):
             pl.call(pl.bwd, "awr_conv_wgrad_simt", x.t, dy, gW, pl.dt, x.N, x.H, x.W, self.Cin, y.H, y.W, self.Cout, self.k, self.k,
                     self.stride, self.pad, 1, self.Cin, self.Cout * self.Cin, flops=self.flops, tag="conv_wgrad", detail=self.detail, side=True)
         if self.bname:
-            pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.arena(ACC * self.Cout), 0, pl.G(self.bname), pl.arena(1))
+            pl.call(pl.bwd, "awr_channel_stats", dy, pl.dt, y.M, self.Cout, pl.arena(ACC * self.Cout), 0, pl.G(self.bname), pl.arena(1),
+                        side=True)          # bias gradient: like the weight gradient, nothing downstream in backward consumes it
         # data gradient
         if True:
             w = pl.P(self.wname)

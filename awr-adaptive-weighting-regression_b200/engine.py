@@ -236,6 +236,7 @@ class Plan:
         self.lib = L.lib()
         self.fwd, self.bwd = [], []
         self.fwd_meta, self.bwd_meta = [], []     # per launch: (kernel entry point, algorithmic flops, algorithmic bytes)
+        self.fwd_side, self._fwd_branch, self._fwd_join = [], False, False      # per forward launch: 0 main, 1 branch stream, 2 main after joining it
         self.bwd_side = []                        # per backward launch: may run on the side stream (weight gradients: nothing downstream
                                                   # in the backward pass consumes them, so they overlap the dgrad / BN chain)
         self._arena_total = 0
@@ -366,6 +367,11 @@ class Plan:
         (self.fwd_meta if lst is self.fwd else self.bwd_meta).append((tag or fn, flops, nbytes, detail))
         if lst is self.bwd:
             self.bwd_side.append(bool(side))
+        else:
+            # forward: launches planned while a branch is open (Hourglass up1) may run on a second stream; a launch flagged `join`
+            # (the add that consumes the branch) waits for it
+            self.fwd_side.append(1 if self._fwd_branch else (2 if self._fwd_join else 0))
+            self._fwd_join = False
 
     def P(self, name):
         return self.store.layout.phys(self.store.params, name)
@@ -389,10 +395,29 @@ class Plan:
     def buf(self, name):
         return self.store.buffers[name]
 
-    def run_forward(self, stream=None):
+    def run_forward(self, stream=None, side=None):
+        """side: optional torch.cuda.Stream for independent branches (Hourglass: each level's full-resolution `up1` Residual runs there
+        while the low-resolution spine -- a chain of small, latency-bound launches -- continues on the main stream; the level's
+        upsample+add joins them).  Without it everything runs in program order on one stream."""
         s = L.stream() if stream is None else stream
-        for f in self.fwd:
-            f(s)
+        if side is None or not any(self.fwd_side):
+            for f in self.fwd:
+                f(s)
+            return
+        main = torch.cuda.current_stream()
+        on_side = False
+        for f, where in zip(self.fwd, self.fwd_side):
+            if where == 1:
+                if not on_side:                  # a branch opens: its input is whatever the main stream has produced so far
+                    side.wait_stream(main)
+                    on_side = True
+                f(side.cuda_stream)
+            else:
+                on_side = False
+                if where == 2:
+                    main.wait_stream(side)
+                f(s)
+        main.wait_stream(side)
 
     def run_backward(self, stream=None, side=None, part=None, join=True):
         """side: optional torch.cuda.Stream.  Launches flagged `side` (weight gradients) are issued there, each after everything
@@ -516,10 +541,13 @@ class Plan:
         return self.add(o, res)
 
     def _hourglass(self, x, p, n):
+        self._fwd_branch = True                  # hourglass.py:79-88: up1 depends only on x, the pool -> low1 -> low2 -> low3 spine likewise
         up1 = self._residual(x, p + ".up1", x.C)
+        self._fwd_branch = False
         low1 = self._residual(self.maxpool(x, 2, 2, 0), p + ".low1", x.C)
         low2 = self._hourglass(low1, p + ".low2", n - 1) if n > 1 else self._residual(low1, p + ".low2", x.C)
         low3 = self._residual(low2, p + ".low3", x.C)
+        self._fwd_join = True
         return self.upsample_add(up1, low3)
 
     def _build_hourglass(self, nstack):

@@ -86,6 +86,8 @@ class FusedTrainer:
         self._skip_cache = {}
         # optimizer per gradient bucket, overlapped with the rest of backward (AWR_B200_OPT_OVERLAP=0: one launch after backward)
         self.opt_overlap = os.environ.get("AWR_B200_OPT_OVERLAP", "1") == "1"
+        # Hourglass: full-resolution up1 branches on a second stream beside the low-resolution spine (AWR_B200_FWD_OVERLAP=0: one stream)
+        self.fwd_overlap = os.environ.get("AWR_B200_FWD_OVERLAP", "1") == "1"
         self.jt = torch.empty(self.B, J, 3, dtype=torch.float32, device=dev)
         ns = len(self.sup_heads)
         self.uvd_all = [torch.empty(self.B, J, 3, dtype=torch.float32, device=dev) for _ in range(ns)]
@@ -119,7 +121,7 @@ class FusedTrainer:
         for h in pl.heads:
             if h not in self.sup_heads:
                 L.check(self.lib.awr_memset_zero(h.dpred.data_ptr(), h.dpred.numel() * 4, s), "awr_memset_zero")
-        pl.run_forward(s)
+        pl.run_forward(s, side=self.side if self.fwd_overlap else None)
         for i, hd in enumerate(self.sup_heads):
             uvd, ws, loss = self.uvd_all[i], self.ws_all[i], self.loss_all[i]
             L.check(self.lib.awr_head_fwd(hd.pred.data_ptr(), L.F32, pl.img.data_ptr(), self.jt.data_ptr(), uvd.data_ptr(),

@@ -173,7 +173,7 @@ class FusedTrainer:
 
     def _allreduce(self):
         if self.world > 1:
-            dp.allreduce_sum_(self.store.grads, self.pg)        # NCCL over NVLink; 1/world is applied inside awr_adam_flat
+            dp.allreduce_sum_(self.store.grads, self.pg)        # NCCL over NVLink; 1/world is applied inside the optimizer kernel
 
     def _overlapped(self):
         """Fallback data-parallel step (AWR_B200_DP_GRAPH=0): graph A -> async NCCL on bucket 1 -> graph B -> async NCCL on bucket 0 ->
